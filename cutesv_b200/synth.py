@@ -1,0 +1,265 @@
+"""Seeded synthetic workloads shaped like BASELINE.json's configs.
+
+Everything is generated directly as the columnar int32 arrays the C-ABI takes (see
+include/cutesv_b200.h): contig ids are ranks of the contig names in Python string order and
+read ids are ranks of zero-padded read names, so id order == the reference's string order.
+
+  config 2: 30x ONT whole genome, INS + DEL      (R = 7.75 M reads, 8 388 608 sigs per type)
+  config 3: 50x HiFi, all five SV types + genotyping
+  config 5: 100x ONT ultra-long (deep pile-ups)
+
+`scale` shrinks genome length, read count and signature counts together so that coverage and
+signature density (what the clustering sees) are preserved at small sizes.
+"""
+import numpy as np
+
+# hg19 contigs of the reference's simulation/LASeR.bed (name, length)
+HG19 = [("1", 249250621), ("2", 243199373), ("3", 198022430), ("4", 191154276), ("5", 180915260),
+        ("6", 171115067), ("7", 159138663), ("8", 146364022), ("9", 141213431), ("10", 135534747),
+        ("11", 135006516), ("12", 133851895), ("13", 115169878), ("14", 107349540),
+        ("15", 102531392), ("16", 90354753), ("17", 81195210), ("18", 78077248), ("19", 59128983),
+        ("20", 63025520), ("21", 48129895), ("22", 51304566), ("X", 155270560), ("Y", 59373566),
+        ("MT", 16569)]
+
+SEED0 = 20260924
+
+
+def contigs(scale=1.0, n_contigs=None):
+    """Contig names sorted in Python string order (id = rank) and their lengths."""
+    tab = HG19 if n_contigs is None else HG19[:n_contigs]
+    tab = sorted(tab, key=lambda x: x[0])
+    names = [t[0] for t in tab]
+    lens = np.array([max(int(t[1] * scale), 2000) for t in tab], dtype=np.int64)
+    return names, lens
+
+
+def read_name(i):
+    return "read%09d" % i
+
+
+def _pick_contig(rng, lens, n):
+    p = lens / lens.sum()
+    return rng.choice(len(lens), size=n, p=p).astype(np.int32)
+
+
+def synth_reads(rng, lens, n_reads, median=9000.0, sigma=0.7, lo=500, hi=200000, primary_frac=0.97,
+                normal=None):
+    """reads_info_list rows (cuteSV:729-733).  Returns dict of columns + per-read arrays."""
+    chrom = _pick_contig(rng, lens, n_reads)
+    if normal is None:
+        length = np.clip(rng.lognormal(np.log(median), sigma, n_reads), lo, hi).astype(np.int64)
+    else:
+        length = np.clip(rng.normal(normal[0], normal[1], n_reads), lo, hi).astype(np.int64)
+    clen = lens[chrom]
+    length = np.minimum(length, np.maximum(clen - 1, 1))
+    start = (rng.random(n_reads) * (clen - length)).astype(np.int64)
+    end = start + length
+    is_primary = (rng.random(n_reads) < primary_frac).astype(np.uint8)
+    read_id = np.arange(n_reads, dtype=np.int32)
+    # supplementary rows carry the name of some primary read
+    sup = np.flatnonzero(is_primary == 0)
+    prim = np.flatnonzero(is_primary == 1)
+    if len(sup) and len(prim):
+        read_id[sup] = prim[rng.integers(0, len(prim), len(sup))]
+    return dict(chrom=chrom, start=start.astype(np.int32), end=end.astype(np.int32), read_id=read_id,
+                is_primary=is_primary)
+
+
+def _covering_index(reads, lens):
+    """Per-contig start-sorted views for 'which reads span position p' queries."""
+    off = np.concatenate([[0], np.cumsum(lens + 1)])
+    lin = off[reads["chrom"]] + reads["start"]
+    order = np.argsort(lin, kind="stable")
+    return off, lin[order], order
+
+
+def _loci_support(rng, reads, lens, loci_chrom, loci_pos, het_p=0.5):
+    """For every locus pick the reads that carry it. Returns (locus_index, read_row) pairs."""
+    off, lin_sorted, order = _covering_index(reads, lens)
+    maxlen = int((reads["end"].astype(np.int64) - reads["start"]).max()) if len(order) else 0
+    lp = off[loci_chrom] + loci_pos
+    lo = np.searchsorted(lin_sorted, lp - maxlen, side="left")
+    hi = np.searchsorted(lin_sorted, lp, side="right")
+    hom = rng.random(len(lp)) < 0.5
+    li, ri = [], []
+    ends = reads["end"].astype(np.int64)
+    starts = reads["start"].astype(np.int64)
+    chrom = reads["chrom"]
+    for k in range(len(lp)):
+        rows = order[lo[k]:hi[k]]
+        if len(rows) == 0:
+            continue
+        rows = rows[(chrom[rows] == loci_chrom[k]) & (starts[rows] + 50 <= loci_pos[k]) &
+                    (ends[rows] - 50 > loci_pos[k])]
+        if len(rows) == 0:
+            continue
+        if not hom[k]:
+            rows = rows[rng.random(len(rows)) < het_p]
+        li.append(np.full(len(rows), k, dtype=np.int64))
+        ri.append(rows)
+    if not li:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    return np.concatenate(li), np.concatenate(ri)
+
+
+def synth_indel(rng, lens, reads, n_sigs, n_loci, svtype, half_frac=0.02, short_seq_frac=0.05,
+                dup_frac=0.002):
+    """DEL / INS signature columns: true loci + uniform noise."""
+    loci_chrom = _pick_contig(rng, lens, n_loci)
+    loci_pos = (rng.random(n_loci) * np.maximum(lens[loci_chrom] - 200, 1)).astype(np.int64) + 100
+    loci_len = np.clip(rng.lognormal(np.log(150.0), 1.0, n_loci), 50, 20000)
+    li, ri = _loci_support(rng, reads, lens, loci_chrom, loci_pos)
+    if len(li) > n_sigs:
+        li, ri = li[:n_sigs], ri[:n_sigs]
+    n_true = len(li)
+    t_chrom = loci_chrom[li]
+    t_pos = np.clip(loci_pos[li] + rng.integers(-15, 16, n_true), 0, lens[t_chrom] - 1)
+    t_len = np.maximum((loci_len[li] * rng.normal(1.0, 0.04, n_true)).astype(np.int64), 10)
+    t_rid = reads["read_id"][ri]
+    n_noise = n_sigs - n_true
+    rr = rng.integers(0, len(reads["chrom"]), n_noise)
+    n_chrom = reads["chrom"][rr]
+    span = np.maximum(reads["end"][rr].astype(np.int64) - reads["start"][rr], 1)
+    n_pos = reads["start"][rr] + (rng.random(n_noise) * span).astype(np.int64)
+    n_len = 10 + rng.geometric(0.15, n_noise)
+    n_rid = reads["read_id"][rr]
+    chrom = np.concatenate([t_chrom, n_chrom]).astype(np.int32)
+    pos = np.concatenate([t_pos, n_pos]).astype(np.int64)
+    length = np.concatenate([t_len, n_len]).astype(np.int32)
+    rid = np.concatenate([t_rid, n_rid]).astype(np.int32)
+    half = (rng.random(len(chrom)) < half_frac).astype(np.int64)
+    seqlen = length.copy()
+    short = rng.random(len(chrom)) < short_seq_frac
+    seqlen[short] = (seqlen[short] * rng.random(int(short.sum()))).astype(np.int32)
+    # exact duplicates (the reference's remove_duplicates_sorted must drop them)
+    nd = int(len(chrom) * dup_frac)
+    if nd:
+        src = rng.integers(0, len(chrom), nd)
+        dst = rng.integers(0, len(chrom), nd)
+        for col in (chrom, pos, length, rid, half, seqlen):
+            col[dst] = col[src]
+    perm = rng.permutation(len(chrom))
+    chrom, pos, length, rid, half, seqlen = (x[perm] for x in (chrom, pos, length, rid, half, seqlen))
+    if svtype == "DEL":
+        return dict(chrom=chrom, a=pos.astype(np.int32), b=length, read_id=rid, c=None)
+    return dict(chrom=chrom, a=(2 * pos + half).astype(np.int32), b=length, read_id=rid, c=seqlen)
+
+
+def synth_dup(rng, lens, reads, n_loci, noise):
+    loci_chrom = _pick_contig(rng, lens, n_loci)
+    size = np.clip(rng.lognormal(np.log(3000.0), 1.0, n_loci), 100, 80000).astype(np.int64)
+    p1 = (rng.random(n_loci) * np.maximum(lens[loci_chrom] - size - 200, 1)).astype(np.int64) + 100
+    li, ri = _loci_support(rng, reads, lens, loci_chrom, p1)
+    n = len(li)
+    a = p1[li] + rng.integers(-20, 21, n)
+    b = p1[li] + size[li] + rng.integers(-20, 21, n)
+    # a second allele on some loci (exercises the pos2 sub-clustering)
+    alt = rng.random(n) < 0.1
+    b[alt] += 2000
+    rr = rng.integers(0, len(reads["chrom"]), noise)
+    na = reads["start"][rr].astype(np.int64) + 10
+    nb = na + rng.integers(50, 5000, noise)
+    chrom = np.concatenate([loci_chrom[li], reads["chrom"][rr]]).astype(np.int32)
+    aa = np.maximum(np.concatenate([a, na]), 0).astype(np.int32)
+    bb = np.concatenate([b, nb]).astype(np.int32)
+    rid = np.concatenate([reads["read_id"][ri], reads["read_id"][rr]]).astype(np.int32)
+    perm = rng.permutation(len(chrom))
+    return dict(chrom=chrom[perm], a=aa[perm], b=bb[perm], read_id=rid[perm], c=None)
+
+
+def synth_inv(rng, lens, reads, n_loci, noise):
+    loci_chrom = _pick_contig(rng, lens, n_loci)
+    size = np.clip(rng.lognormal(np.log(5000.0), 1.0, n_loci), 100, 90000).astype(np.int64)
+    p1 = (rng.random(n_loci) * np.maximum(lens[loci_chrom] - size - 200, 1)).astype(np.int64) + 100
+    cols = []
+    for strand in (0, 1):
+        li, ri = _loci_support(rng, reads, lens, loci_chrom, p1 if strand == 0 else p1 + size)
+        n = len(li)
+        a = p1[li] + rng.integers(-30, 31, n) + strand * 3
+        b = p1[li] + size[li] + rng.integers(-30, 31, n) + strand * 3
+        cols.append((loci_chrom[li], a, b, reads["read_id"][ri], np.full(n, strand)))
+    rr = rng.integers(0, len(reads["chrom"]), noise)
+    na = reads["start"][rr].astype(np.int64) + 10
+    cols.append((reads["chrom"][rr], na, na + rng.integers(50, 5000, noise), reads["read_id"][rr],
+                 rng.integers(0, 2, noise)))
+    chrom = np.concatenate([c[0] for c in cols]).astype(np.int32)
+    a = np.maximum(np.concatenate([c[1] for c in cols]), 0).astype(np.int32)
+    b = np.concatenate([c[2] for c in cols]).astype(np.int32)
+    rid = np.concatenate([c[3] for c in cols]).astype(np.int32)
+    st = np.concatenate([c[4] for c in cols]).astype(np.int32)
+    perm = rng.permutation(len(chrom))
+    return dict(chrom=chrom[perm], a=a[perm], b=b[perm], read_id=rid[perm], c=st[perm])
+
+
+def synth_tra(rng, lens, reads, n_loci, noise):
+    loci_chrom = _pick_contig(rng, lens, n_loci)
+    chr2 = _pick_contig(rng, lens, n_loci)
+    typ = rng.integers(0, 4, n_loci)
+    p1 = (rng.random(n_loci) * np.maximum(lens[loci_chrom] - 400, 1)).astype(np.int64) + 100
+    p2 = (rng.random(n_loci) * np.maximum(lens[chr2] - 400, 1)).astype(np.int64) + 100
+    li, ri = _loci_support(rng, reads, lens, loci_chrom, p1)
+    n = len(li)
+    a = p1[li] + rng.integers(-10, 11, n)
+    b = p2[li] + rng.integers(-10, 11, n)
+    alt = rng.random(n) < 0.15  # second mate-position allele
+    b[alt] += 500
+    c = chr2[li] * 4 + typ[li]
+    rr = rng.integers(0, len(reads["chrom"]), noise)
+    nc2 = _pick_contig(rng, lens, noise)
+    na = reads["start"][rr].astype(np.int64) + 10
+    nb = (rng.random(noise) * np.maximum(lens[nc2] - 10, 1)).astype(np.int64)
+    ncc = nc2 * 4 + rng.integers(0, 4, noise)
+    chrom = np.concatenate([loci_chrom[li], reads["chrom"][rr]]).astype(np.int32)
+    aa = np.maximum(np.concatenate([a, na]), 0).astype(np.int32)
+    bb = np.maximum(np.concatenate([b, nb]), 0).astype(np.int32)
+    rid = np.concatenate([reads["read_id"][ri], reads["read_id"][rr]]).astype(np.int32)
+    cc = np.concatenate([c, ncc]).astype(np.int32)
+    perm = rng.permutation(len(chrom))
+    return dict(chrom=chrom[perm], a=aa[perm], b=bb[perm], read_id=rid[perm], c=cc[perm])
+
+
+def make_config(config_id=2, scale=1.0, seed=None):
+    """Build one of BASELINE.json's synthetic configs.
+
+    Returns dict(names, lens, reads, sigs={type_name: cols}, params=dict(...), n_sigs).
+    """
+    rng = np.random.default_rng((SEED0 + config_id) if seed is None else seed)
+    names, lens = contigs(scale)
+    sigs = {}
+    if config_id in (2, 4):
+        n_reads = max(int(7750000 * scale), 200)
+        n_sigs = max(int(8388608 * scale), 64)
+        n_loci = max(int(20000 * scale), 4)
+        reads = synth_reads(rng, lens, n_reads)
+        sigs["DEL"] = synth_indel(rng, lens, reads, n_sigs, n_loci, "DEL")
+        sigs["INS"] = synth_indel(rng, lens, reads, n_sigs, n_loci, "INS")
+        # ONT preset (cuteSV_Description.py:30-46) + --genotype
+        params = dict(min_support=10, bias_ins=100, ratio_ins=0.3, bias_del=100, ratio_del=0.3, genotype=1)
+    elif config_id == 3:
+        n_reads = max(int(8600000 * scale), 200)
+        reads = synth_reads(rng, lens, n_reads, normal=(18000.0, 3000.0), lo=1000, hi=60000)
+        n_loci = max(int(25000 * scale), 4)
+        n_sigs = max(int(8388608 * scale / 20) + n_loci * 50, 64)
+        sigs["DEL"] = synth_indel(rng, lens, reads, n_sigs, n_loci, "DEL")
+        sigs["INS"] = synth_indel(rng, lens, reads, n_sigs, n_loci, "INS")
+        sigs["DUP"] = synth_dup(rng, lens, reads, max(int(3000 * scale), 2), max(int(20000 * scale), 8))
+        sigs["INV"] = synth_inv(rng, lens, reads, max(int(300 * scale), 2), max(int(5000 * scale), 8))
+        sigs["TRA"] = synth_tra(rng, lens, reads, max(int(300 * scale), 2), max(int(5000 * scale), 8))
+        # HiFi preset + --genotype
+        params = dict(min_support=3, bias_ins=1000, ratio_ins=0.9, bias_del=1000, ratio_del=0.5, genotype=1)
+    elif config_id == 5:
+        n_reads = max(int(3100000 * scale), 200)
+        reads = synth_reads(rng, lens, n_reads, median=60000.0, sigma=0.9, lo=1000, hi=1000000)
+        n_loci = max(int(20000 * scale), 4)
+        n_sigs = max(int(3 * 8388608 * scale), 64)
+        sigs["DEL"] = synth_indel(rng, lens, reads, n_sigs, n_loci, "DEL")
+        sigs["INS"] = synth_indel(rng, lens, reads, n_sigs, n_loci, "INS")
+        sigs["DUP"] = synth_dup(rng, lens, reads, max(int(2000 * scale), 2), max(int(20000 * scale), 8))
+        sigs["INV"] = synth_inv(rng, lens, reads, max(int(300 * scale), 2), max(int(5000 * scale), 8))
+        sigs["TRA"] = synth_tra(rng, lens, reads, max(int(300 * scale), 2), max(int(5000 * scale), 8))
+        params = dict(min_support=10, bias_ins=100, ratio_ins=0.3, bias_del=100, ratio_del=0.3, genotype=1)
+    else:
+        raise ValueError("config_id must be 2, 3, 4 or 5")
+    n_total = int(sum(len(v["chrom"]) for v in sigs.values()))
+    return dict(names=names, lens=lens, reads=reads, sigs=sigs, params=params, n_sigs=n_total,
+                config_id=config_id, scale=scale)

@@ -1,0 +1,196 @@
+"""Runs the UNMODIFIED reference (/root/reference/src) on columnar inputs (TEST INFRASTRUCTURE).
+
+Only usable in the authoring container: /root/reference does not exist on the GPU box, so this
+module is imported by oracle/gen_golden.py (which commits its outputs under tests/golden/) and
+by tests that skip themselves when the reference is absent.
+
+pysam / cigar / Bio are not installed here; they are stubbed with the minimal surface the hot
+path touches.
+"""
+import importlib.machinery
+import importlib.util
+import os
+import pickle
+import re
+import sys
+import tempfile
+import types
+
+REF_SRC = "/root/reference/src"
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_SRC, "cuteSV"))
+
+
+def _install_stubs():
+    if "pysam" not in sys.modules:
+        m = types.ModuleType("pysam")
+        (m.CMATCH, m.CINS, m.CDEL, m.CREF_SKIP, m.CSOFT_CLIP, m.CHARD_CLIP, m.CPAD, m.CEQUAL, m.CDIFF,
+         m.CBACK) = range(10)
+        sys.modules["pysam"] = m
+    if "cigar" not in sys.modules:
+        m = types.ModuleType("cigar")
+
+        class Cigar(object):  # PyPI "Cigar": Cigar(s).items() -> (length, op) pairs
+            def __init__(self, s):
+                self.s = s
+
+            def items(self):
+                for n, op in re.findall(r"(\d+)([MIDNSHP=X])", self.s):
+                    yield (int(n), op)
+        m.Cigar = Cigar
+        sys.modules["cigar"] = m
+    if "Bio" not in sys.modules:
+        bio = types.ModuleType("Bio")
+        seqm = types.ModuleType("Bio.Seq")
+        comp = str.maketrans("ACGTNacgtn", "TGCANtgcan")
+
+        class Seq(object):
+            def __init__(self, s):
+                self.s = s
+
+            def reverse_complement(self):
+                return Seq(self.s.translate(comp)[::-1])
+
+            def __str__(self):
+                return self.s
+        seqm.Seq = Seq
+        bio.Seq = seqm
+        sys.modules["Bio"] = bio
+        sys.modules["Bio.Seq"] = seqm
+
+
+_mods = {}
+
+
+def modules():
+    """(main_script_module, resolveINDEL, resolveDUP, resolveINV, resolveTRA, genotype)."""
+    if not _mods:
+        if not available():
+            raise RuntimeError("reference not present at %s" % REF_SRC)
+        _install_stubs()
+        if REF_SRC not in sys.path:
+            sys.path.insert(0, REF_SRC)
+        from cuteSV import cuteSV_genotype, cuteSV_resolveDUP, cuteSV_resolveINDEL, cuteSV_resolveINV, cuteSV_resolveTRA
+        loader = importlib.machinery.SourceFileLoader("cutesv_ref_main", os.path.join(REF_SRC, "cuteSV", "cuteSV"))
+        spec = importlib.util.spec_from_loader("cutesv_ref_main", loader)
+        main = importlib.util.module_from_spec(spec)
+        loader.exec_module(main)
+        _mods.update(main=main, indel=cuteSV_resolveINDEL, dup=cuteSV_resolveDUP, inv=cuteSV_resolveINV,
+                     tra=cuteSV_resolveTRA, genotype=cuteSV_genotype)
+    return _mods
+
+
+def ins_seq_of(key, n):
+    """Deterministic synthetic INS sequence of length n.  `key` must be a function of the
+    signature's content (see ins_key) so that identical tuples carry identical sequences."""
+    pat = "ACGT"
+    k = key % 4
+    s = (pat[k:] + pat[:k]) * (n // 4 + 1)
+    return s[:n]
+
+
+def ins_key(ins_cols, i):
+    return int(ins_cols["a"][i]) + int(ins_cols["read_id"][i]) + int(ins_cols["b"][i])
+
+
+def ins_seq_fn(ins_cols):
+    """idx -> synthetic sequence of INS signature idx (what a host packer would hold)."""
+    return lambda i: ins_seq_of(ins_key(ins_cols, i), int(ins_cols["c"][i]))
+
+
+def to_tuples(sigs, reads, chrom_names, read_name):
+    """Columnar arrays -> the reference's tuple lists (cuteSV:520-531,235-239,55-60,111-117,733)."""
+    out = {k: [] for k in ("DEL", "INS", "DUP", "INV", "TRA")}
+    s = sigs.get("DEL")
+    if s is not None:
+        for i in range(len(s["chrom"])):
+            out["DEL"].append((int(s["a"][i]), int(s["b"][i]), read_name(int(s["read_id"][i])), "DEL",
+                               chrom_names[int(s["chrom"][i])]))
+    s = sigs.get("INS")
+    if s is not None:
+        for i in range(len(s["chrom"])):
+            a = int(s["a"][i])
+            pos = a // 2 if a % 2 == 0 else a / 2
+            out["INS"].append((pos, int(s["b"][i]), read_name(int(s["read_id"][i])), ins_seq_of(ins_key(s, i), int(s["c"][i])),
+                               "INS", chrom_names[int(s["chrom"][i])]))
+    s = sigs.get("DUP")
+    if s is not None:
+        for i in range(len(s["chrom"])):
+            out["DUP"].append((int(s["a"][i]), int(s["b"][i]), read_name(int(s["read_id"][i])), "DUP",
+                               chrom_names[int(s["chrom"][i])]))
+    s = sigs.get("INV")
+    if s is not None:
+        for i in range(len(s["chrom"])):
+            out["INV"].append(("++" if int(s["c"][i]) == 0 else "--", int(s["a"][i]), int(s["b"][i]),
+                               read_name(int(s["read_id"][i])), "INV", chrom_names[int(s["chrom"][i])]))
+    s = sigs.get("TRA")
+    if s is not None:
+        for i in range(len(s["chrom"])):
+            c = int(s["c"][i])
+            out["TRA"].append(("ABCD"[c & 3], int(s["a"][i]), chrom_names[c >> 2], int(s["b"][i]),
+                               read_name(int(s["read_id"][i])), "TRA", chrom_names[int(s["chrom"][i])]))
+    rl = []
+    if reads is not None:
+        for i in range(len(reads["chrom"])):
+            rl.append((int(reads["start"][i]), int(reads["end"][i]), int(reads["is_primary"][i]),
+                       read_name(int(reads["read_id"][i])), chrom_names[int(reads["chrom"][i])]))
+    out["reads"] = rl
+    return out
+
+
+def run_reference(sigs, reads, chrom_names, read_name, p, types_=("DEL", "INS", "INV", "DUP", "TRA"),
+                  n_pids=1):
+    """Reference rebuild (process_process_sigs_type, cuteSV:750-857) + clustering phase
+    (cuteSV:1113-1199, run serially).  p: csv_params.  Returns {(type, chrom): rows}.
+
+    TRA is run with action=False (its call_gt needs a BAM)."""
+    m = modules()
+    main = m["main"]
+    tuples = to_tuples(sigs, reads, chrom_names, read_name)
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        tmp = d + "/"
+        os.mkdir(tmp + "signatures")
+        pids = list(range(100, 100 + n_pids))
+        for k in ("DEL", "INS", "DUP", "INV", "TRA", "reads"):
+            lst = tuples[k]
+            for j, pid in enumerate(pids):  # round-robin "tasks" over fake worker pids
+                with open("%ssignatures/%s%s.pickle" % (tmp, pid, k), "ab") as f:
+                    pickle.dump(lst[j::n_pids], f)
+        sigs_index = {}
+        for k in ("DEL", "INS", "DUP", "INV", "TRA", "reads"):
+            r = main.process_process_sigs_type((k, tmp, pids, False))
+            sigs_index[r[0]] = r[1]
+            if r[0] == "reads":
+                sigs_index["reads_count"] = r[2]
+        action = bool(p.genotype)
+        if "DEL" in types_:
+            for chr_ in sigs_index["DEL"]:
+                c, rows = m["indel"].run_del((tmp, chr_, "DEL", p.min_support, p.ratio_del, p.bias_del,
+                                              p.min_support_allele, "", action, p.gt_round, p.remain_reads_ratio,
+                                              sigs_index))
+                res[("DEL", c)] = rows
+        if "INS" in types_:
+            for chr_ in sigs_index["INS"]:
+                c, rows = m["indel"].run_ins((tmp, chr_, "INS", p.min_support, p.ratio_ins, p.bias_ins,
+                                              p.min_support_allele, "", action, p.gt_round, p.remain_reads_ratio,
+                                              sigs_index))
+                res[("INS", c)] = rows
+        if "INV" in types_:
+            for chr_ in sigs_index["INV"]:
+                c, rows = m["inv"].run_inv((tmp, chr_, "INV", p.min_support, p.bias_inv, p.min_size, "", action,
+                                            p.max_size, p.gt_round, sigs_index))
+                res[("INV", c)] = rows
+        if "DUP" in types_:
+            for chr_ in sigs_index["DUP"]:
+                c, rows = m["dup"].run_dup((tmp, chr_, p.min_support, p.bias_dup, p.min_size, "", action,
+                                            p.max_size, p.gt_round, sigs_index))
+                res[("DUP", c)] = rows
+        if "TRA" in types_:
+            for chr_ in sigs_index["TRA"]:
+                c, rows = m["tra"].run_tra((tmp, chr_, p.min_support, p.ratio_tra, p.bias_tra, "", False,
+                                            p.gt_round, sigs_index))
+                res[("TRA", c)] = rows
+    return res
