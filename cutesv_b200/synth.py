@@ -263,3 +263,75 @@ def make_config(config_id=2, scale=1.0, seed=None):
     n_total = int(sum(len(v["chrom"]) for v in sigs.values()))
     return dict(names=names, lens=lens, reads=reads, sigs=sigs, params=params, n_sigs=n_total,
                 config_id=config_id, scale=scale)
+
+
+def adversarial(seed, n_contigs=3, max_sigs=400):
+    """Small dense cases that hit the reference's quirks: ties in pos/len, many signatures per
+    read, pile-ups, odd biases, tiny supports, x.5 INS positions, short INS seqs, duplicates."""
+    rng = np.random.default_rng(seed)
+    names, lens = contigs(1.0, n_contigs)
+    lens = np.minimum(lens, 200000).astype(np.int64)
+    n_reads = int(rng.integers(5, 120))
+    span = int(rng.choice([300, 2000, 30000]))
+    base = rng.integers(0, 50000, n_contigs)
+    rc = rng.integers(0, n_contigs, n_reads).astype(np.int32)
+    rs = np.maximum(base[rc] - rng.integers(0, 20000, n_reads), 0)
+    re_ = base[rc] + span + rng.integers(-span // 2, 20000, n_reads)
+    re_ = np.maximum(re_, rs + 1)
+    prim = (rng.random(n_reads) < 0.85).astype(np.uint8)
+    rid = np.arange(n_reads, dtype=np.int32)
+    sup = np.flatnonzero(prim == 0)
+    pr = np.flatnonzero(prim == 1)
+    if len(sup) and len(pr):
+        rid[sup] = pr[rng.integers(0, len(pr), len(sup))]
+    reads = dict(chrom=rc, start=rs.astype(np.int32), end=re_.astype(np.int32), read_id=rid, is_primary=prim)
+    if rng.random() < 0.1:  # a contig without any reads-table row (call_gt returns [])
+        keep = rc != 0
+        reads = {k: v[keep] for k, v in reads.items()}
+
+    def col(n, kind):
+        chrom = rng.integers(0, n_contigs, n).astype(np.int32)
+        a = base[chrom] + rng.integers(0, span, n)
+        r = rng.integers(0, n_reads, n).astype(np.int32)
+        if kind in ("DEL", "INS"):
+            b = rng.choice([rng.integers(10, 60, n), rng.integers(10, 2000, n),
+                            np.full(n, 50) + rng.integers(0, 3, n)][int(rng.integers(0, 3))], n)
+            b = np.asarray(b).astype(np.int32)
+            if kind == "DEL":
+                return dict(chrom=chrom, a=a.astype(np.int32), b=b, read_id=r, c=None)
+            half = (rng.random(n) < 0.2).astype(np.int64)
+            c = np.where(rng.random(n) < 0.3, (b * rng.random(n)).astype(np.int32), b).astype(np.int32)
+            return dict(chrom=chrom, a=(2 * a + half).astype(np.int32), b=b, read_id=r, c=c)
+        if kind == "DUP":
+            b = a + rng.integers(0, 3000, n)
+            return dict(chrom=chrom, a=a.astype(np.int32), b=b.astype(np.int32), read_id=r, c=None)
+        if kind == "INV":
+            b = a + rng.integers(-100, 3000, n)
+            return dict(chrom=chrom, a=a.astype(np.int32), b=np.maximum(b, 0).astype(np.int32), read_id=r,
+                        c=rng.integers(0, 2, n).astype(np.int32))
+        c2 = rng.integers(0, n_contigs, n)
+        b = base[c2] + rng.integers(0, span, n)
+        return dict(chrom=chrom, a=a.astype(np.int32), b=b.astype(np.int32), read_id=r,
+                    c=(c2 * 4 + rng.integers(0, 4, n)).astype(np.int32))
+
+    sigs = {}
+    for kind in ("DEL", "INS", "INV", "DUP", "TRA"):
+        n = int(rng.integers(0, max_sigs))
+        s = col(n, kind)
+        if n > 4:  # exact duplicates
+            nd = n // 10
+            src, dst = rng.integers(0, n, nd), rng.integers(0, n, nd)
+            for k, v in s.items():
+                if v is not None:
+                    v[dst] = v[src]
+        sigs[kind] = s
+    ms = int(rng.choice([1, 2, 3, 5, 10]))
+    params = dict(min_support=ms, min_size=int(rng.choice([0, 30, 50])), max_size=int(rng.choice([-1, 1000, 100000])),
+                  bias_del=int(rng.choice([7, 100, 200, 1000])), bias_ins=int(rng.choice([5, 100, 1001])),
+                  bias_inv=int(rng.choice([11, 500])), bias_dup=int(rng.choice([13, 500])),
+                  bias_tra=int(rng.choice([3, 50, 501])), ratio_del=float(rng.choice([0.0, 0.3, 0.5, 0.9])),
+                  ratio_ins=float(rng.choice([0.0, 0.3, 0.9])), ratio_tra=float(rng.choice([0.3, 0.6, 0.9])),
+                  remain_reads_ratio=float(rng.choice([1.0, 1.0, 0.7, 0.5, 0.01, 2.0])),
+                  genotype=int(rng.random() < 0.8))
+    return dict(names=names, lens=lens, reads=reads, sigs=sigs, params=params,
+                n_sigs=int(sum(len(v["chrom"]) for v in sigs.values())), config_id=0, scale=0.0)
