@@ -1,0 +1,822 @@
+// cutesv_b200.cu -- C-ABI (include/cutesv_b200.h) and host orchestration of the sm_100a kernels.
+//
+// One translation unit: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo.
+// There is deliberately no host compute path in this library: without a usable GPU csv_create
+// fails (CSV_E_NODEVICE) and every other entry point needs a ctx.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/cutesv_b200.h"
+#include "core.h"
+#include "devprims.cuh"
+#include "host_tables.h"
+#include "kernels.cuh"
+#include "radix.cuh"
+#include "extract.cuh"
+
+using namespace csv;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                               \
+    do {                                                                                                       \
+        cudaError_t e__ = (call);                                                                              \
+        if (e__ != cudaSuccess)                                                                                \
+            return set_err(CSV_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* csv_last_error(void) { return g_err; }
+extern "C" int csv_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------
+// device buffers
+// ------------------------------------------------------------------------------------------
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, bool zero_new = false) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); if (e != cudaSuccess) return e; p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return e;
+        cap = want;
+        if (zero_new) return cudaMemset(p, 0, want);
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct SigBuf {
+    int64_t n = 0;
+    bool has_c = false;
+    DBuf chrom, a, b, rid, c;
+};
+
+struct SmallWork {  // DUP / INV / TRA
+    DBuf k_rid, k_b, k_prim, perm_a, perm_b, sel, u_chrom, u_a, u_b, u_rid, u_c;
+};
+
+struct csv_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int n_sm = 148;
+    csv_params P;
+    bool have_params = false;
+    // contigs
+    int32_t n_contigs = 0;
+    std::vector<int64_t> contig_len;
+    std::vector<uint64_t> contig_off;
+    int64_t off_pad = 0;
+    DBuf d_off, d_len;
+    // inputs
+    SigBuf sig[CSV_NTYPES];
+    int64_t n_reads = 0;
+    DBuf r_chrom, r_start, r_end, r_id, r_prim;
+    // sort workspace
+    DBuf keys_a, keys_b, vals_a, vals_b, hist, lb_status, tickets;
+    uint32_t gen = 1;
+    int ticket_next = 0;
+    SmallWork small;
+    // segment / cluster
+    DBuf kept[CSV_NTYPES], big_list, giant_list, giant_arena, cnt;
+    uint32_t kept_cap[CSV_NTYPES] = {0, 0, 0, 0, 0};
+    // results
+    DBuf cand_tmp, cand, geno, names, counters;
+    uint32_t cap_cand = 0, cap_names = 0;
+    Counters* h_counters = nullptr;  // pinned
+    // genotype
+    DBuf bin_start, bin_fill, win_list, dr, has_rows, gl_table, pow_half;
+    uint32_t pow_n = 0;
+    // state
+    bool ran = false, counts_valid = false;
+    int64_t launches = 0;
+    // profiling: CUDA-event intervals on the ctx stream; a stage may be entered once per SV type
+    bool profiling = false;
+    struct Interval { int st; cudaEvent_t a, b; int64_t bytes; };
+    std::vector<Interval> ivs;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_next = 0;
+    bool ivs_consumed = false;
+    float stage_ms[CSV_ST_COUNT];
+    float sort_ms = 0.f;
+    int64_t sort_bytes = 0;
+    int32_t sort_launches = 0;
+    uint32_t last_mask = 0x1f;
+    // extraction
+    ExtractState ex;
+};
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
+    do {                                                                               \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);               \
+        (ctx)->launches++;                                                             \
+    } while (0)
+
+static int grid_for(const csv_ctx* c, int64_t n, int block, int per_sm = 8) {
+    int64_t g = (n + block - 1) / block;
+    int64_t cap = (int64_t)c->n_sm * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+static int bits_for(uint64_t max_value) {
+    int b = 0;
+    while (b < 64 && (max_value >> b) != 0) b++;
+    return b < 1 ? 1 : b;
+}
+
+// ------------------------------------------------------------------------------------------
+// profiling helpers
+// ------------------------------------------------------------------------------------------
+static constexpr int ST_SORT_PASS = CSV_ST_COUNT;  // pseudo stage: one onesweep launch
+static cudaEvent_t pool_event(csv_ctx* c) {
+    if (c->ev_next == c->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[c->ev_next++];
+}
+static void stage_reset_if_consumed(csv_ctx* c) {
+    if (c->ivs_consumed) { c->ivs.clear(); c->ev_next = 0; c->ivs_consumed = false; }
+}
+static void stage_begin(csv_ctx* c, int st, int64_t bytes = 0) {
+    if (!c->profiling) return;
+    stage_reset_if_consumed(c);
+    csv_ctx::Interval iv;
+    iv.st = st; iv.a = pool_event(c); iv.b = pool_event(c); iv.bytes = bytes;
+    cudaEventRecord(iv.a, c->stream);
+    c->ivs.push_back(iv);
+}
+static void stage_end(csv_ctx* c, int st) {
+    if (!c->profiling) return;
+    for (size_t i = c->ivs.size(); i-- > 0;)
+        if (c->ivs[i].st == st) { cudaEventRecord(c->ivs[i].b, c->stream); return; }
+}
+static void stage_collect(csv_ctx* c) {  // after a stream synchronize
+    for (int s = 0; s < CSV_ST_COUNT; s++) c->stage_ms[s] = 0.f;
+    c->sort_ms = 0.f; c->sort_bytes = 0; c->sort_launches = 0;
+    for (const csv_ctx::Interval& iv : c->ivs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, iv.a, iv.b) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (iv.st == ST_SORT_PASS) { c->sort_ms += t; c->sort_bytes += iv.bytes; c->sort_launches++; }
+        else c->stage_ms[iv.st] += t;
+    }
+    c->ivs_consumed = true;
+}
+
+// ------------------------------------------------------------------------------------------
+// create / destroy / params
+// ------------------------------------------------------------------------------------------
+extern "C" int csv_default_params(csv_params* p) {
+    if (!p) return set_err(CSV_E_INVALID, "null params");
+    memset(p, 0, sizeof(*p));
+    p->min_support = 10; p->min_support_allele = 5; p->min_size = 30; p->max_size = 100000;
+    p->bias_del = 200; p->bias_ins = 100; p->bias_inv = 500; p->bias_dup = 500; p->bias_tra = 50;
+    p->genotype = 0; p->gt_round = 500; p->gt_bias_ins = 1000;
+    p->ratio_del = 0.5; p->ratio_ins = 0.3; p->ratio_tra = 0.6; p->remain_reads_ratio = 1.0;
+    p->min_mapq = 20; p->max_split_parts = 7; p->min_read_len = 500; p->min_siglength = 10;
+    p->merge_del_threshold = 0; p->merge_ins_threshold = 100;
+    return CSV_OK;
+}
+
+static int upload_tables(csv_ctx* c, uint32_t pow_n) {
+    std::vector<csv_geno> gl = build_gl_table();
+    CU(c->gl_table.ensure(gl.size() * sizeof(csv_geno)));
+    CU(cudaMemcpy(c->gl_table.p, gl.data(), gl.size() * sizeof(csv_geno), cudaMemcpyHostToDevice));
+    std::vector<double> ph = build_pow_half(pow_n);
+    CU(c->pow_half.ensure(ph.size() * sizeof(double)));
+    CU(cudaMemcpy(c->pow_half.p, ph.data(), ph.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->pow_n = pow_n;
+    return CSV_OK;
+}
+
+extern "C" int csv_create(int device, void* stream, csv_ctx** out) {
+    if (!out) return set_err(CSV_E_INVALID, "null out");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return set_err(CSV_E_NODEVICE, "no CUDA device (%s): cutesv_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return set_err(CSV_E_INVALID, "device %d out of range (%d devices)", device, n_dev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return set_err(CSV_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+    csv_ctx* c = new csv_ctx();
+    c->device = device;
+    c->n_sm = prop.multiProcessorCount;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else {
+        cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e2 != cudaSuccess) { delete c; return set_err(CSV_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
+        c->own_stream = true;
+    }
+    csv_default_params(&c->P);
+    for (int s = 0; s < CSV_ST_COUNT; s++) c->stage_ms[s] = 0.f;
+    cudaError_t e3 = cudaMallocHost((void**)&c->h_counters, sizeof(Counters));
+    if (e3 != cudaSuccess) { delete c; return set_err(CSV_E_CUDA, "cudaMallocHost: %s", cudaGetErrorString(e3)); }
+    int rc = upload_tables(c, 1u << 16);
+    if (rc != CSV_OK) { delete c; return rc; }
+    // opt in to large dynamic shared memory for the cluster kernels
+    CU(cudaFuncSetAttribute(k_cluster_warp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (CL_THREADS / 32) * WARP_M * ARENA_PER_MAX + (CL_THREADS / 32) * 40 * 8));
+    CU(cudaFuncSetAttribute(k_cluster_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
+    *out = c;
+    return CSV_OK;
+}
+
+extern "C" int csv_destroy(csv_ctx* c) {
+    if (!c) return CSV_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DBuf* all[] = {&c->d_off, &c->d_len, &c->r_chrom, &c->r_start, &c->r_end, &c->r_id, &c->r_prim, &c->keys_a, &c->keys_b,
+                   &c->vals_a, &c->vals_b, &c->hist, &c->lb_status, &c->tickets, &c->big_list, &c->giant_list, &c->giant_arena,
+                   &c->cnt, &c->cand_tmp, &c->cand, &c->geno, &c->names, &c->counters, &c->bin_start, &c->bin_fill, &c->win_list,
+                   &c->dr, &c->has_rows, &c->gl_table, &c->pow_half, &c->small.k_rid, &c->small.k_b, &c->small.k_prim,
+                   &c->small.perm_a, &c->small.perm_b, &c->small.sel, &c->small.u_chrom, &c->small.u_a, &c->small.u_b,
+                   &c->small.u_rid, &c->small.u_c};
+    for (DBuf* b : all) b->release();
+    for (int t = 0; t < CSV_NTYPES; t++) {
+        c->sig[t].chrom.release(); c->sig[t].a.release(); c->sig[t].b.release(); c->sig[t].rid.release(); c->sig[t].c.release();
+        c->kept[t].release();
+    }
+    extract_release(&c->ex);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return CSV_OK;
+}
+
+extern "C" int csv_set_params(csv_ctx* c, const csv_params* p) {
+    if (!c || !p) return set_err(CSV_E_INVALID, "null argument");
+    if (p->min_support < 1) return set_err(CSV_E_INVALID, "min_support must be >= 1");
+    if (p->bias_del < 1 || p->bias_ins < 1 || p->bias_inv < 1 || p->bias_dup < 1 || p->bias_tra < 1 || p->gt_bias_ins < 1)
+        return set_err(CSV_E_INVALID, "max_cluster_bias_* must be >= 1");
+    const int64_t old_pad = c->off_pad;
+    c->P = *p;
+    c->have_params = true;
+    c->counts_valid = false;
+    // the linear coordinate pads every contig by more than the largest bias
+    int64_t pad = std::max<int64_t>({p->bias_del, p->bias_ins, p->bias_inv, p->bias_dup, p->bias_tra, p->gt_bias_ins}) + 1;
+    if (pad != old_pad && c->n_contigs > 0) {
+        std::vector<int64_t> lens = c->contig_len;
+        c->off_pad = pad;
+        return csv_set_contigs(c, (int32_t)lens.size(), lens.data());
+    }
+    c->off_pad = pad;
+    return CSV_OK;
+}
+
+extern "C" int csv_set_contigs(csv_ctx* c, int32_t n, const int64_t* lens) {
+    if (!c || n < 1 || !lens) return set_err(CSV_E_INVALID, "bad contig table");
+    CU(cudaSetDevice(c->device));
+    if (c->off_pad == 0) csv_set_params(c, &c->P);
+    c->n_contigs = n;
+    c->contig_len.assign(lens, lens + n);
+    c->contig_off.resize(n + 1);
+    uint64_t run = 0;
+    for (int i = 0; i < n; i++) {
+        if (lens[i] < 0 || lens[i] >= (1ll << 31)) return set_err(CSV_E_INVALID, "contig %d length %lld out of range", i, (long long)lens[i]);
+        c->contig_off[i] = run;
+        run += (uint64_t)lens[i] + (uint64_t)c->off_pad;
+    }
+    c->contig_off[n] = run;
+    CU(c->d_off.ensure((n + 1) * sizeof(uint64_t)));
+    CU(c->d_len.ensure(n * sizeof(int64_t)));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(c->d_off.p, c->contig_off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_len.p, c->contig_len.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice));
+    c->counts_valid = false;
+    return CSV_OK;
+}
+
+extern "C" int csv_host_alloc(void** p, size_t bytes) {
+    if (!p) return set_err(CSV_E_INVALID, "null");
+    CU(cudaMallocHost(p, bytes ? bytes : 1));
+    return CSV_OK;
+}
+extern "C" int csv_host_free(void* p) { if (p) CU(cudaFreeHost(p)); return CSV_OK; }
+extern "C" int csv_host_register(void* p, size_t bytes) { CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); return CSV_OK; }
+extern "C" int csv_host_unregister(void* p) { CU(cudaHostUnregister(p)); return CSV_OK; }
+
+extern "C" int csv_set_profiling(csv_ctx* c, int on) {
+    if (!c) return set_err(CSV_E_INVALID, "null ctx");
+    CU(cudaSetDevice(c->device));
+    c->profiling = on != 0;
+    return CSV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// uploads
+// ------------------------------------------------------------------------------------------
+extern "C" int csv_upload_sigs(csv_ctx* c, int t, const csv_sig_cols* h) {
+    if (!c || t < 0 || t >= CSV_NTYPES || !h) return set_err(CSV_E_INVALID, "bad argument");
+    if (h->n < 0 || h->n >= (1ll << 30)) return set_err(CSV_E_INVALID, "signature count %lld out of range", (long long)h->n);
+    CU(cudaSetDevice(c->device));
+    SigBuf& s = c->sig[t];
+    s.n = h->n;
+    s.has_c = h->c != nullptr;
+    c->counts_valid = false;
+    if (h->n == 0) return CSV_OK;
+    if (!h->chrom || !h->a || !h->b || !h->read_id) return set_err(CSV_E_INVALID, "null column");
+    if ((t == CSV_INS || t == CSV_INV || t == CSV_TRA) && !h->c) return set_err(CSV_E_INVALID, "column c is required for INS/INV/TRA");
+    const size_t bytes = (size_t)h->n * 4;
+    stage_begin(c, CSV_ST_H2D);
+    CU(s.chrom.ensure(bytes)); CU(s.a.ensure(bytes)); CU(s.b.ensure(bytes)); CU(s.rid.ensure(bytes));
+    CU(cudaMemcpyAsync(s.chrom.p, h->chrom, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(s.a.p, h->a, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(s.b.p, h->b, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(s.rid.p, h->read_id, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (h->c) { CU(s.c.ensure(bytes)); CU(cudaMemcpyAsync(s.c.p, h->c, bytes, cudaMemcpyHostToDevice, c->stream)); }
+    stage_end(c, CSV_ST_H2D);
+    return CSV_OK;
+}
+
+extern "C" int csv_upload_reads(csv_ctx* c, const csv_reads_cols* h) {
+    if (!c || !h) return set_err(CSV_E_INVALID, "bad argument");
+    if (h->n < 0 || h->n >= (1ll << 31)) return set_err(CSV_E_INVALID, "read count out of range");
+    CU(cudaSetDevice(c->device));
+    c->n_reads = h->n;
+    c->counts_valid = false;
+    if (h->n == 0) return CSV_OK;
+    if (!h->chrom || !h->start || !h->end || !h->read_id || !h->is_primary) return set_err(CSV_E_INVALID, "null column");
+    const size_t bytes = (size_t)h->n * 4;
+    stage_begin(c, CSV_ST_H2D);
+    CU(c->r_chrom.ensure(bytes)); CU(c->r_start.ensure(bytes)); CU(c->r_end.ensure(bytes)); CU(c->r_id.ensure(bytes));
+    CU(c->r_prim.ensure((size_t)h->n));
+    CU(cudaMemcpyAsync(c->r_chrom.p, h->chrom, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->r_start.p, h->start, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->r_end.p, h->end, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->r_id.p, h->read_id, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->r_prim.p, h->is_primary, (size_t)h->n, cudaMemcpyHostToDevice, c->stream));
+    stage_end(c, CSV_ST_H2D);
+    return CSV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// look-back sync objects
+// ------------------------------------------------------------------------------------------
+static int make_sync(csv_ctx* c, size_t status_words, TileSync* ts) {
+    if (c->ticket_next >= 1024) return set_err(CSV_E_STATE, "ticket pool exhausted");
+    if (c->lb_status.cap < status_words * 8) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(c->lb_status.ensure(status_words * 8, true));
+    }
+    ts->ticket = c->tickets.as<uint32_t>() + c->ticket_next++;
+    ts->status = c->lb_status.as<uint64_t>();
+    ts->gen = ++c->gen;
+    return CSV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// radix sort driver: sorts (keys_a, vals_a) using (keys_b, vals_b) as the ping-pong partner.
+// vals_a == nullptr on input means "payload = iota".  Outputs point at the final buffers.
+// ------------------------------------------------------------------------------------------
+template <typename K>
+static int radix_sort(csv_ctx* c, K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* vals_b, bool iota, int64_t n,
+                      const uint32_t* n_dev, int bits, K** keys_out, uint32_t** vals_out) {
+    const int passes = std::max(1, (bits + 7) / 8);
+    if (passes > RS_MAX_PASSES) return set_err(CSV_E_INVALID, "radix sort: %d bits", bits);
+    constexpr int TILE = RS_THREADS * RsTraits<K>::ITEMS;
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    CU(c->hist.ensure(RS_MAX_PASSES * 256 * 4));
+    CU(cudaMemsetAsync(c->hist.p, 0, RS_MAX_PASSES * 256 * 4, c->stream));
+    LAUNCH(c, (k_rs_hist<K>), grid_for(c, n, RS_THREADS * 16, 4), RS_THREADS, 0, keys_a, n, n_dev, passes, c->hist.as<uint32_t>());
+    LAUNCH(c, k_rs_hist_scan, 1, 256, 0, c->hist.as<uint32_t>(), passes);
+    K* ki = keys_a; K* ko = keys_b;
+    uint32_t* vi = vals_a; uint32_t* vo = vals_b;
+    for (int p = 0; p < passes; p++) {
+        TileSync ts;
+        int rc = make_sync(c, (size_t)n_tiles * 256, &ts);
+        if (rc) return rc;
+        stage_begin(c, ST_SORT_PASS, n * (int64_t)(sizeof(K) + ((p == 0 && iota) ? 0 : 4) + sizeof(K) + 4));
+        if (p == 0 && iota)
+            LAUNCH(c, (k_rs_onesweep<K, true>), (int)n_tiles, RS_THREADS, 0, ki, (const uint32_t*)nullptr, ko, vo, n, n_dev, 8 * p,
+                   c->hist.as<uint32_t>() + p * 256, ts.status, ts.gen, ts.ticket);
+        else
+            LAUNCH(c, (k_rs_onesweep<K, false>), (int)n_tiles, RS_THREADS, 0, ki, vi, ko, vo, n, n_dev, 8 * p,
+                   c->hist.as<uint32_t>() + p * 256, ts.status, ts.gen, ts.ticket);
+        stage_end(c, ST_SORT_PASS);
+        std::swap(ki, ko);
+        std::swap(vi, vo);
+    }
+    *keys_out = ki;
+    *vals_out = vi;
+    return CSV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the pipeline
+// ------------------------------------------------------------------------------------------
+static ClusterParams cluster_params(const csv_params& P, int t) {
+    ClusterParams C;
+    C.min_support = P.min_support;
+    C.min_support_allele = P.min_support_allele;
+    C.min_size = P.min_size;
+    C.max_size = P.max_size;
+    C.bias = t == CSV_DEL ? P.bias_del : t == CSV_INS ? P.bias_ins : t == CSV_INV ? P.bias_inv : t == CSV_DUP ? P.bias_dup : P.bias_tra;
+    C.ratio = t == CSV_DEL ? P.ratio_del : t == CSV_INS ? P.ratio_ins : P.ratio_tra;
+    C.keep = P.remain_reads_ratio > 1 ? 1 : P.remain_reads_ratio;
+    C.genotype = P.genotype;
+    return C;
+}
+
+static Emit make_emit(csv_ctx* c) {
+    Emit E;
+    E.cand = c->cand_tmp.as<csv_cand>();
+    E.names = c->names.as<int32_t>();
+    E.cnt = c->cnt.as<uint32_t>();
+    E.ctr = c->counters.as<Counters>();
+    E.pow_half = c->pow_half.as<double>();
+    E.lim.cap_cand = c->cap_cand;
+    E.lim.cap_names = c->cap_names;
+    E.lim.pow_n = c->pow_n;
+    return E;
+}
+
+static int run_segment_and_cluster(csv_ctx* c, TypeJob& J, int t, uint32_t kslot_base) {
+    Counters* ctr = c->counters.as<Counters>();
+    // ---- segment: kept chain clusters, in order ----
+    stage_begin(c, CSV_ST_SEGMENT);
+    J.kslot_base = kslot_base;
+    J.kept_start = c->kept[t].as<uint32_t>();
+    J.big_list = c->big_list.as<uint32_t>();
+    J.giant_list = c->giant_list.as<uint32_t>();
+    J.giant_arena = c->giant_arena.as<char>();
+    TileSync ts;
+    int rc = make_sync(c, (size_t)(J.n_host / SEL_TILE + 2), &ts);
+    if (rc) return rc;
+    HeadPred hp{J};
+    LAUNCH(c, (k_select<HeadPred>), grid_for(c, J.n_host, SEL_TILE, 4), SEL_THREADS, 0, hp, J.n_host, J.n_dev,
+           c->kept[t].as<uint32_t>(), c->kept_cap[t], &ctr->n_kept[t], ts, &ctr->status, (uint32_t)ST_LIST_OVERFLOW);
+    stage_end(c, CSV_ST_SEGMENT);
+    // ---- cluster ----
+    stage_begin(c, CSV_ST_CLUSTER);
+    Emit E = make_emit(c);
+    const size_t smem_warp = (size_t)(CL_THREADS / 32) * WARP_M * ARENA_PER_MAX + (CL_THREADS / 32) * 40 * 8;
+    LAUNCH(c, k_cluster_warp, c->n_sm * 2, CL_THREADS, smem_warp, J, E, ctr);
+    LAUNCH(c, (k_cluster_block<false>), c->n_sm, CL_THREADS, (size_t)BLOCK_M * ARENA_PER_MAX, J, E, ctr);
+    LAUNCH(c, (k_cluster_block<true>), c->n_sm, CL_THREADS, 0, J, E, ctr);
+    stage_end(c, CSV_ST_CLUSTER);
+    return CSV_OK;
+}
+
+static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
+    SigBuf& s = c->sig[t];
+    const int64_t n = s.n;
+    const uint64_t total = c->contig_off[c->n_contigs];
+    const int bits = bits_for(total);
+    const bool k64 = bits > 32;
+    ContigTab ct{c->d_off.as<uint64_t>(), c->d_len.as<int64_t>(), c->n_contigs};
+    Counters* ctr = c->counters.as<Counters>();
+    TypeJob J;
+    memset(&J, 0, sizeof(J));
+    J.svtype = t; J.n_host = n; J.n_dev = nullptr;
+    J.cp = cluster_params(c->P, t);
+    stage_begin(c, CSV_ST_KEYS);
+    if (!k64)
+        LAUNCH(c, (k_indel_keys<uint32_t>), grid_for(c, n, 256), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(),
+               s.rid.as<int32_t>(), n, t == CSV_INS ? 1 : 0, ct, c->keys_a.as<uint32_t>(), &ctr->status);
+    else
+        LAUNCH(c, (k_indel_keys<uint64_t>), grid_for(c, n, 256), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(),
+               s.rid.as<int32_t>(), n, t == CSV_INS ? 1 : 0, ct, c->keys_a.as<uint64_t>(), &ctr->status);
+    stage_end(c, CSV_ST_KEYS);
+    stage_begin(c, CSV_ST_SORT);
+    uint32_t* sidx = nullptr;
+    int rc;
+    if (!k64) {
+        uint32_t* ko = nullptr;
+        rc = radix_sort<uint32_t>(c, c->keys_a.as<uint32_t>(), c->vals_a.as<uint32_t>(), c->keys_b.as<uint32_t>(),
+                                  c->vals_b.as<uint32_t>(), true, n, nullptr, bits, &ko, &sidx);
+        J.keys32 = ko;
+    } else {
+        uint64_t* ko = nullptr;
+        rc = radix_sort<uint64_t>(c, c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), c->keys_b.as<uint64_t>(),
+                                  c->vals_b.as<uint32_t>(), true, n, nullptr, bits, &ko, &sidx);
+        J.keys64 = ko;
+    }
+    if (rc) return rc;
+    stage_end(c, CSV_ST_SORT);
+    J.iv.chrom = s.chrom.as<int32_t>(); J.iv.a = s.a.as<int32_t>(); J.iv.b = s.b.as<int32_t>(); J.iv.rid = s.rid.as<int32_t>();
+    J.iv.c = s.has_c ? s.c.as<int32_t>() : nullptr;
+    J.iv.sidx = sidx;
+    J.iv.is_ins = t == CSV_INS ? 1 : 0;
+    return run_segment_and_cluster(c, J, t, kslot_base);
+}
+
+static int run_other(csv_ctx* c, int t, uint32_t kslot_base) {
+    SigBuf& s = c->sig[t];
+    const int64_t n = s.n;
+    SmallWork& w = c->small;
+    ContigTab ct{c->d_off.as<uint64_t>(), c->d_len.as<int64_t>(), c->n_contigs};
+    Counters* ctr = c->counters.as<Counters>();
+    const int cb = bits_for((uint64_t)c->n_contigs);
+    if (t == CSV_TRA && cb > 13) return set_err(CSV_E_INVALID, "TRA: more than 8191 contigs are not supported");
+    const int prim_bits = 31 + (t == CSV_DUP ? cb : t == CSV_INV ? cb + 1 : cb + 20);
+    const int32_t* col_c = s.has_c ? s.c.as<int32_t>() : nullptr;
+    stage_begin(c, CSV_ST_KEYS);
+    LAUNCH(c, k_other_keys, grid_for(c, n, 256), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(), s.rid.as<int32_t>(),
+           col_c, n, t, ct, w.k_rid.as<uint32_t>(), w.k_b.as<uint32_t>(), w.k_prim.as<uint64_t>(), &ctr->status);
+    stage_end(c, CSV_ST_KEYS);
+    // LSD over the fields of the reference's tuple sort key: name, then second coordinate, then primary
+    stage_begin(c, CSV_ST_SORT);
+    uint32_t *k32o = nullptr, *perm = nullptr;
+    LAUNCH(c, (k_gather_keys<uint32_t>), grid_for(c, n, 256), 256, 0, w.k_rid.as<uint32_t>(), (const uint32_t*)nullptr, n, c->keys_a.as<uint32_t>());
+    int rc = radix_sort<uint32_t>(c, c->keys_a.as<uint32_t>(), c->vals_a.as<uint32_t>(), c->keys_b.as<uint32_t>(), c->vals_b.as<uint32_t>(),
+                                  true, n, nullptr, 31, &k32o, &perm);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(w.perm_a.p, perm, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    LAUNCH(c, (k_gather_keys<uint32_t>), grid_for(c, n, 256), 256, 0, w.k_b.as<uint32_t>(), w.perm_a.as<uint32_t>(), n, c->keys_a.as<uint32_t>());
+    CU(cudaMemcpyAsync(c->vals_a.p, w.perm_a.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    rc = radix_sort<uint32_t>(c, c->keys_a.as<uint32_t>(), c->vals_a.as<uint32_t>(), c->keys_b.as<uint32_t>(), c->vals_b.as<uint32_t>(),
+                              false, n, nullptr, 31, &k32o, &perm);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(w.perm_a.p, perm, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    LAUNCH(c, (k_gather_keys<uint64_t>), grid_for(c, n, 256), 256, 0, w.k_prim.as<uint64_t>(), w.perm_a.as<uint32_t>(), n, c->keys_a.as<uint64_t>());
+    CU(cudaMemcpyAsync(c->vals_a.p, w.perm_a.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    uint64_t* k64o = nullptr;
+    rc = radix_sort<uint64_t>(c, c->keys_a.as<uint64_t>(), c->vals_a.as<uint32_t>(), c->keys_b.as<uint64_t>(), c->vals_b.as<uint32_t>(),
+                              false, n, nullptr, prim_bits, &k64o, &perm);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(w.perm_b.p, perm, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    stage_end(c, CSV_ST_SORT);
+    // exact-duplicate removal + materialise the sorted columns
+    stage_begin(c, CSV_ST_SEGMENT);
+    uint32_t* n_u = &ctr->pad[t - CSV_INV];  // device-side size of the de-duplicated domain (one slot per small type)
+    TileSync ts;
+    rc = make_sync(c, (size_t)(n / SEL_TILE + 2), &ts);
+    if (rc) return rc;
+    DedupPred dp{s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(), s.rid.as<int32_t>(), col_c, w.perm_b.as<uint32_t>()};
+    LAUNCH(c, (k_select<DedupPred>), grid_for(c, n, SEL_TILE, 4), SEL_THREADS, 0, dp, n, (const uint32_t*)nullptr, w.sel.as<uint32_t>(),
+           (uint32_t)n, n_u, ts, &ctr->status, (uint32_t)ST_INTERNAL);
+    LAUNCH(c, k_other_gather, grid_for(c, n, 256), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(), s.rid.as<int32_t>(),
+           col_c, w.perm_b.as<uint32_t>(), w.sel.as<uint32_t>(), n_u, w.u_chrom.as<int32_t>(), w.u_a.as<int32_t>(), w.u_b.as<int32_t>(),
+           w.u_rid.as<int32_t>(), w.u_c.as<int32_t>());
+    stage_end(c, CSV_ST_SEGMENT);
+    TypeJob J;
+    memset(&J, 0, sizeof(J));
+    J.svtype = t; J.n_host = n; J.n_dev = n_u;
+    J.cp = cluster_params(c->P, t);
+    J.sv.chrom = w.u_chrom.as<int32_t>(); J.sv.a = w.u_a.as<int32_t>(); J.sv.b = w.u_b.as<int32_t>();
+    J.sv.rid = w.u_rid.as<int32_t>(); J.sv.c = w.u_c.as<int32_t>();
+    return run_segment_and_cluster(c, J, t, kslot_base);
+}
+
+static int ensure_workspace(csv_ctx* c, uint32_t type_mask) {
+    int64_t n_max = 0, n_total = 0, n_small_max = 0;
+    for (int t = 0; t < CSV_NTYPES; t++) {
+        if (!(type_mask >> t & 1)) continue;
+        n_max = std::max(n_max, c->sig[t].n);
+        n_total += c->sig[t].n;
+        if (t >= CSV_INV) n_small_max = std::max(n_small_max, c->sig[t].n);
+    }
+    const size_t nm = (size_t)std::max<int64_t>(n_max, 1);
+    CU(c->keys_a.ensure(nm * 8)); CU(c->keys_b.ensure(nm * 8)); CU(c->vals_a.ensure(nm * 4)); CU(c->vals_b.ensure(nm * 4));
+    CU(c->tickets.ensure(1024 * 4));
+    CU(c->counters.ensure(sizeof(Counters)));
+    const size_t ns = (size_t)std::max<int64_t>(n_small_max, 1);
+    SmallWork& w = c->small;
+    CU(w.k_rid.ensure(ns * 4)); CU(w.k_b.ensure(ns * 4)); CU(w.k_prim.ensure(ns * 8)); CU(w.perm_a.ensure(ns * 4)); CU(w.perm_b.ensure(ns * 4));
+    CU(w.sel.ensure(ns * 4)); CU(w.u_chrom.ensure(ns * 4)); CU(w.u_a.ensure(ns * 4)); CU(w.u_b.ensure(ns * 4)); CU(w.u_rid.ensure(ns * 4));
+    CU(w.u_c.ensure(ns * 4));
+    uint64_t kept_total = 0;
+    const int ms = std::max(1, c->P.min_support);
+    for (int t = 0; t < CSV_NTYPES; t++) {
+        if (!(type_mask >> t & 1)) continue;
+        c->kept_cap[t] = (uint32_t)(c->sig[t].n / ms + 1);
+        CU(c->kept[t].ensure((size_t)c->kept_cap[t] * 4));
+        kept_total += c->kept_cap[t];
+    }
+    CU(c->cnt.ensure((size_t)kept_total * 4 + 4));
+    CU(c->big_list.ensure((nm / WARP_M + 2) * 4));
+    CU(c->giant_list.ensure((nm / BLOCK_M + 2) * 4));
+    CU(c->giant_arena.ensure(nm * 2 * ARENA_PER_MAX + 256));
+    const int ms_a = std::max(1, std::min(c->P.min_support, std::max(1, c->P.min_support_allele)));
+    c->cap_cand = (uint32_t)(n_total / ms_a + 16);
+    c->cap_names = (uint32_t)(n_total + 16);
+    CU(c->cand_tmp.ensure((size_t)c->cap_cand * sizeof(csv_cand)));
+    CU(c->cand.ensure((size_t)c->cap_cand * sizeof(csv_cand)));
+    CU(c->geno.ensure((size_t)c->cap_cand * sizeof(csv_geno)));
+    CU(c->names.ensure((size_t)c->cap_names * 4));
+    CU(c->dr.ensure((size_t)c->cap_cand * 4));
+    CU(c->win_list.ensure((size_t)c->cap_cand * 2 * 4));
+    CU(c->has_rows.ensure((size_t)c->n_contigs + 16));
+    return CSV_OK;
+}
+
+extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
+    if (!c) return set_err(CSV_E_INVALID, "null ctx");
+    if (c->n_contigs == 0) return set_err(CSV_E_STATE, "csv_set_contigs has not been called");
+    CU(cudaSetDevice(c->device));
+    int rc = ensure_workspace(c, type_mask);
+    if (rc) return rc;
+    stage_reset_if_consumed(c);
+    c->last_mask = type_mask;
+    c->ticket_next = 0;
+    CU(cudaMemsetAsync(c->tickets.p, 0, 1024 * 4, c->stream));
+    CU(cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), c->stream));
+    CU(cudaMemsetAsync(c->cnt.p, 0, c->cnt.cap, c->stream));
+    Counters* ctr = c->counters.as<Counters>();
+    uint32_t kslot_base = 0;
+    for (int t = 0; t < CSV_NTYPES; t++) {
+        if (!(type_mask >> t & 1) || c->sig[t].n == 0) continue;
+        rc = (t == CSV_DEL || t == CSV_INS) ? run_indel(c, t, kslot_base) : run_other(c, t, kslot_base);
+        if (rc) return rc;
+        kslot_base += c->kept_cap[t];
+    }
+    // ---- order ----
+    stage_begin(c, CSV_ST_ORDER);
+    {
+        TileSync ts;
+        rc = make_sync(c, (size_t)(kslot_base / SEL_TILE + 2), &ts);
+        if (rc) return rc;
+        LAUNCH(c, k_scan_excl, grid_for(c, std::max<int64_t>(kslot_base, 1), SEL_TILE, 2), SEL_THREADS, 0, c->cnt.as<uint32_t>(),
+               (int64_t)kslot_base, (const uint32_t*)nullptr, (uint32_t*)nullptr, ts);
+        LAUNCH(c, k_permute, grid_for(c, c->cap_cand, 256, 4), 256, 0, c->cand_tmp.as<csv_cand>(), c->cnt.as<uint32_t>(), ctr, c->cap_cand,
+               c->cand.as<csv_cand>());
+    }
+    stage_end(c, CSV_ST_ORDER);
+    // ---- genotype ----
+    stage_begin(c, CSV_ST_GENOTYPE);
+    {
+        GenoJob G;
+        memset(&G, 0, sizeof(G));
+        const uint64_t total = c->contig_off[c->n_contigs];
+        int shift = 10;
+        while ((total >> shift) > (1u << 18)) shift++;
+        G.cand = c->cand.as<csv_cand>(); G.geno = c->geno.as<csv_geno>(); G.names = c->names.as<int32_t>(); G.ctr = ctr;
+        G.cap_cand = c->cap_cand;
+        G.ct = ContigTab{c->d_off.as<uint64_t>(), c->d_len.as<int64_t>(), c->n_contigs};
+        G.gp = GtParams{c->P.bias_del, c->P.gt_bias_ins, c->P.bias_dup, c->P.bias_inv};
+        G.shift = shift;
+        G.n_bins = (uint32_t)(total >> shift) + 2;
+        CU(c->bin_start.ensure(((size_t)G.n_bins + 1) * 4));
+        CU(c->bin_fill.ensure((size_t)G.n_bins * 4));
+        G.bin_start = c->bin_start.as<uint32_t>(); G.bin_fill = c->bin_fill.as<uint32_t>();
+        G.win_list = c->win_list.as<uint32_t>(); G.win_cap = c->cap_cand * 2;
+        G.dr = c->dr.as<uint32_t>(); G.has_rows = c->has_rows.as<uint8_t>();
+        G.gl_table = c->gl_table.as<csv_geno>();
+        G.genotype = c->P.genotype;
+        if (c->P.genotype) {
+            CU(cudaMemsetAsync(G.bin_start, 0, ((size_t)G.n_bins + 1) * 4, c->stream));
+            CU(cudaMemsetAsync(G.bin_fill, 0, (size_t)G.n_bins * 4, c->stream));
+            CU(cudaMemsetAsync(G.has_rows, 0, (size_t)c->n_contigs, c->stream));
+            LAUNCH(c, (k_windows<0>), grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
+            TileSync ts;
+            rc = make_sync(c, (size_t)((G.n_bins + 1) / SEL_TILE + 2), &ts);
+            if (rc) return rc;
+            LAUNCH(c, k_scan_excl, grid_for(c, G.n_bins + 1, SEL_TILE, 2), SEL_THREADS, 0, G.bin_start, (int64_t)G.n_bins + 1,
+                   (const uint32_t*)nullptr, (uint32_t*)nullptr, ts);
+            LAUNCH(c, (k_windows<1>), grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
+            if (c->n_reads > 0)
+                LAUNCH(c, k_reads_pass, grid_for(c, c->n_reads, 256, 16), 256, 0, G, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                       c->r_end.as<int32_t>(), c->r_id.as<int32_t>(), c->r_prim.as<uint8_t>(), c->n_reads, &ctr->status);
+        }
+        LAUNCH(c, k_finalize, grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
+    }
+    stage_end(c, CSV_ST_GENOTYPE);
+    CU(cudaGetLastError());
+    c->ran = true;
+    c->counts_valid = false;
+    return CSV_OK;
+}
+
+static int finish(csv_ctx* c) {
+    if (!c->ran) return set_err(CSV_E_STATE, "csv_cluster has not been called");
+    if (c->counts_valid) return CSV_OK;
+    CU(cudaMemcpyAsync(c->h_counters, c->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const uint32_t st = c->h_counters->status;
+    if (st & (ST_BAD_CHROM | ST_BAD_POS | ST_NEG_FIELD))
+        return set_err(CSV_E_INPUT, "input validation failed on the device: %s%s%s", (st & ST_BAD_CHROM) ? "[contig id out of range] " : "",
+                       (st & ST_BAD_POS) ? "[position outside its contig] " : "", (st & ST_NEG_FIELD) ? "[negative field] " : "");
+    if (st & ST_POW_TABLE) {
+        // an allele with more supporting reads than the n**0.5 table: grow the table and rerun
+        uint32_t need = c->h_counters->max_support + 1;
+        uint32_t pn = c->pow_n;
+        while (pn <= need) pn *= 2;
+        int rc = upload_tables(c, pn);
+        if (rc) return rc;
+        return 1;  // rerun
+    }
+    if (st) return set_err(CSV_E_CUDA, "internal pipeline error, status 0x%x (cand %u/%u names %u/%u)", st, c->h_counters->n_cand, c->cap_cand,
+                           c->h_counters->n_names, c->cap_names);
+    c->counts_valid = true;
+    return CSV_OK;
+}
+
+extern "C" int csv_result_counts(csv_ctx* c, int64_t* n_cand, int64_t* n_names) {
+    if (!c) return set_err(CSV_E_INVALID, "null ctx");
+    CU(cudaSetDevice(c->device));
+    int rc = finish(c);
+    while (rc == 1) {  // table grown: rerun on the same device-resident inputs
+        rc = csv_cluster(c, c->last_mask);
+        if (rc) return rc;
+        rc = finish(c);
+    }
+    if (rc) return rc;
+    if (n_cand) *n_cand = c->h_counters->n_cand;
+    if (n_names) *n_names = c->h_counters->n_names;
+    return CSV_OK;
+}
+
+extern "C" int csv_fetch(csv_ctx* c, csv_cand* cands, csv_geno* genos, int64_t cap_cand, int32_t* names, int64_t cap_names) {
+    int64_t nc = 0, nn = 0;
+    int rc = csv_result_counts(c, &nc, &nn);
+    if (rc) return rc;
+    if (nc > cap_cand || nn > cap_names) return set_err(CSV_E_CAPACITY, "need %lld candidates / %lld names", (long long)nc, (long long)nn);
+    stage_begin(c, CSV_ST_D2H);
+    if (nc) {
+        CU(cudaMemcpyAsync(cands, c->cand.p, (size_t)nc * sizeof(csv_cand), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(genos, c->geno.p, (size_t)nc * sizeof(csv_geno), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (nn) CU(cudaMemcpyAsync(names, c->names.p, (size_t)nn * 4, cudaMemcpyDeviceToHost, c->stream));
+    stage_end(c, CSV_ST_D2H);
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->profiling) stage_collect(c);
+    return CSV_OK;
+}
+
+extern "C" int csv_result_device_ptrs(csv_ctx* c, const csv_cand** cands, const csv_geno** genos, const int32_t** names) {
+    if (!c || !c->ran) return set_err(CSV_E_STATE, "no results");
+    if (cands) *cands = c->cand.as<csv_cand>();
+    if (genos) *genos = c->geno.as<csv_geno>();
+    if (names) *names = c->names.as<int32_t>();
+    return CSV_OK;
+}
+
+extern "C" int csv_cluster_host(csv_ctx* c, const csv_sig_cols sigs[CSV_NTYPES], const csv_reads_cols* reads, uint32_t type_mask,
+                                csv_cand* cands, csv_geno* genos, int64_t cap_cand, int32_t* names, int64_t cap_names, int64_t* n_cand,
+                                int64_t* n_names) {
+    if (!c || !sigs) return set_err(CSV_E_INVALID, "null argument");
+    int rc;
+    for (int t = 0; t < CSV_NTYPES; t++) {
+        if (!(type_mask >> t & 1)) continue;
+        rc = csv_upload_sigs(c, t, &sigs[t]);
+        if (rc) return rc;
+    }
+    if (reads) { rc = csv_upload_reads(c, reads); if (rc) return rc; }
+    rc = csv_cluster(c, type_mask);
+    if (rc) return rc;
+    int64_t nc = 0, nn = 0;
+    rc = csv_result_counts(c, &nc, &nn);
+    if (rc) return rc;
+    if (n_cand) *n_cand = nc;
+    if (n_names) *n_names = nn;
+    return csv_fetch(c, cands, genos, cap_cand, names, cap_names);
+}
+
+extern "C" int csv_cal_gl(csv_ctx* c, const int32_t* c0, const int32_t* c1, int64_t n, csv_geno* out) {
+    if (!c || !c0 || !c1 || !out || n < 0) return set_err(CSV_E_INVALID, "bad argument");
+    if (n == 0) return CSV_OK;
+    CU(cudaSetDevice(c->device));
+    int32_t *d0 = nullptr, *d1 = nullptr;
+    csv_geno* dg = nullptr;
+    CU(cudaMalloc(&d0, n * 4)); CU(cudaMalloc(&d1, n * 4)); CU(cudaMalloc(&dg, n * sizeof(csv_geno)));
+    CU(cudaMemcpyAsync(d0, c0, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d1, c1, n * 4, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_cal_gl, grid_for(c, n, 256), 256, 0, d0, d1, n, c->gl_table.as<csv_geno>(), dg);
+    CU(cudaMemcpyAsync(out, dg, n * sizeof(csv_geno), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d0); cudaFree(d1); cudaFree(dg);
+    return CSV_OK;
+}
+
+extern "C" int csv_stage_ms(csv_ctx* c, float ms[CSV_ST_COUNT]) {
+    if (!c || !ms) return set_err(CSV_E_INVALID, "null argument");
+    for (int s = 0; s < CSV_ST_COUNT; s++) ms[s] = c->stage_ms[s];
+    return CSV_OK;
+}
+extern "C" int64_t csv_launch_count(csv_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int csv_sort_probe(csv_ctx* c, float* ms_total, int64_t* bytes_total, int32_t* launches) {
+    if (!c) return set_err(CSV_E_INVALID, "null ctx");
+    if (ms_total) *ms_total = c->sort_ms;
+    if (bytes_total) *bytes_total = c->sort_bytes;
+    if (launches) *launches = c->sort_launches;
+    return CSV_OK;
+}
+
+#include "extract_api.inl"

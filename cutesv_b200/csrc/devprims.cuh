@@ -1,0 +1,162 @@
+// devprims.cuh -- device-wide building blocks: decoupled look-back, ordered select, exclusive scan.
+//
+// All kernels here take their element count either from the host (n_host) or from a device
+// counter written by an earlier kernel (n_dev != nullptr), so that the whole pipeline can be
+// enqueued without any host round trip.  Tiles are handed out by an atomic ticket, which makes
+// the spin-wait of the look-back safe: every lower ticket belongs to a CTA that already runs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace csv {
+
+static constexpr uint32_t LB_LOCAL = 1u << 30;
+static constexpr uint32_t LB_INCL = 2u << 30;
+static constexpr uint32_t LB_MASK = (1u << 30) - 1;
+
+// Status words are 64-bit: [generation:32][flag:2][value:30].  Every launch that uses the
+// look-back gets a fresh generation number from the host, so the status buffer never has to be
+// cleared: words of older generations simply read as "not published yet".
+__device__ __forceinline__ uint64_t lb_word(uint32_t gen, uint32_t flag_value) { return ((uint64_t)gen << 32) | flag_value; }
+__device__ __forceinline__ uint32_t lb_wait(volatile uint64_t* p, uint32_t gen) {
+    uint64_t v;
+    do { v = *p; } while ((uint32_t)(v >> 32) != gen || (((uint32_t)v) >> 30) == 0);
+    return (uint32_t)v;
+}
+
+// One thread publishes `local` for `tile` and returns the exclusive prefix over tiles < tile.
+__device__ __forceinline__ uint32_t lookback_exclusive(volatile uint64_t* status, uint32_t gen, int tile, uint32_t local) {
+    if (tile == 0) {
+        status[0] = lb_word(gen, local | LB_INCL);
+        return 0;
+    }
+    status[tile] = lb_word(gen, local | LB_LOCAL);
+    uint32_t excl = 0;
+    for (int p = tile - 1; p >= 0; p--) {
+        const uint32_t v = lb_wait(status + p, gen);
+        excl += v & LB_MASK;
+        if ((v >> 30) == 2) break;
+    }
+    status[tile] = lb_word(gen, (excl + local) | LB_INCL);
+    return excl;
+}
+
+// exclusive scan of one value per thread across a 256-thread CTA; returns exclusive prefix,
+// *total = CTA sum.  s_warp: 9 words of shared memory.
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < 8 ? s_warp[lane] : 0;
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += y;
+        }
+        if (lane < 8) s_warp[lane] = wi - w;
+        if (lane == 7) s_warp[8] = wi;
+    }
+    __syncthreads();
+    uint32_t r = s_warp[warp] + incl - v;
+    *total = s_warp[8];
+    __syncthreads();
+    return r;
+}
+
+static constexpr int SEL_THREADS = 256;
+static constexpr int SEL_ITEMS = 8;
+static constexpr int SEL_TILE = SEL_THREADS * SEL_ITEMS;
+
+struct TileSync {
+    uint32_t* ticket;    // 1 word, zero at launch
+    uint64_t* status;    // >= n_tiles words, never cleared (generation-tagged)
+    uint32_t gen;        // unique per launch
+};
+
+// Ordered select: out[k] = i for the k-th i in [0, n) with pred(i); *out_count = number selected.
+// Overflowing out_cap sets `overflow_bit` in *status_word (and keeps counting).
+template <class Pred>
+__global__ void __launch_bounds__(SEL_THREADS) k_select(Pred pred, int64_t n_host, const uint32_t* n_dev, uint32_t* out,
+                                                        uint32_t out_cap, uint32_t* out_count, TileSync ts,
+                                                        uint32_t* status_word, uint32_t overflow_bit) {
+    __shared__ uint32_t s_warp[9];
+    __shared__ uint32_t s_tile, s_excl;
+    const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ts.ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        const int64_t base = (int64_t)tile * SEL_TILE;
+        if (base >= n) break;
+        const int64_t i0 = base + (int64_t)threadIdx.x * SEL_ITEMS;
+        uint32_t flags = 0, cnt = 0;
+#pragma unroll
+        for (int j = 0; j < SEL_ITEMS; j++) {
+            const int64_t i = i0 + j;
+            if (i < n && pred(i)) { flags |= 1u << j; cnt++; }
+        }
+        uint32_t total;
+        const uint32_t local = block_excl_scan_256(cnt, s_warp, &total);
+        if (threadIdx.x == 0) {
+            s_excl = lookback_exclusive(ts.status, ts.gen, (int)tile, total);
+            if (base + SEL_TILE >= n) *out_count = s_excl + total;
+        }
+        __syncthreads();
+        uint32_t o = s_excl + local;
+#pragma unroll
+        for (int j = 0; j < SEL_ITEMS; j++) {
+            if (flags >> j & 1u) {
+                if (o < out_cap) out[o] = (uint32_t)(i0 + j);
+                else atomicOr(status_word, overflow_bit);
+                o++;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// In-place exclusive scan of arr[0..n); *total_out (nullable) receives the sum.
+__global__ void __launch_bounds__(SEL_THREADS) k_scan_excl(uint32_t* arr, int64_t n_host, const uint32_t* n_dev,
+                                                           uint32_t* total_out, TileSync ts) {
+    __shared__ uint32_t s_warp[9];
+    __shared__ uint32_t s_tile, s_excl;
+    const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ts.ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        const int64_t base = (int64_t)tile * SEL_TILE;
+        if (base >= n) break;
+        const int64_t i0 = base + (int64_t)threadIdx.x * SEL_ITEMS;
+        uint32_t v[SEL_ITEMS], cnt = 0;
+#pragma unroll
+        for (int j = 0; j < SEL_ITEMS; j++) {
+            v[j] = (i0 + j < n) ? arr[i0 + j] : 0u;
+            cnt += v[j];
+        }
+        uint32_t total;
+        const uint32_t local = block_excl_scan_256(cnt, s_warp, &total);
+        if (threadIdx.x == 0) {
+            s_excl = lookback_exclusive(ts.status, ts.gen, (int)tile, total);
+            if (total_out && base + SEL_TILE >= n) *total_out = s_excl + total;
+        }
+        __syncthreads();
+        uint32_t run = s_excl + local;
+#pragma unroll
+        for (int j = 0; j < SEL_ITEMS; j++) {
+            if (i0 + j < n) arr[i0 + j] = run;
+            run += v[j];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace csv

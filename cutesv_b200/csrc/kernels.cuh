@@ -1,0 +1,389 @@
+// kernels.cuh -- the pipeline's kernels around core.h:
+//   keys      (contig, pos) -> one linear sortable coordinate (+ input validation)
+//   segment   chain-linkage boundary votes (max_cluster_bias_*) + ordered compaction of the
+//             clusters that can reach min_support
+//   cluster   one warp / one CTA / one CTA with global scratch per kept cluster -> core.h
+//   order     candidates into the reference's emission order
+//   genotype  windows binned on the linear coordinate, ONE streaming pass over the reads table,
+//             cal_GL through the host-built libm table
+#pragma once
+#include "core.h"
+#include "devprims.cuh"
+
+namespace csv {
+
+static constexpr int WARP_M = 128;    // largest cluster a warp-sized team handles (shared memory)
+static constexpr int BLOCK_M = 2048;  // largest cluster a CTA-sized team handles in shared memory
+static constexpr int CL_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------
+// description of one SV type's sorted domain, passed by value to the kernels
+// ------------------------------------------------------------------------------------------
+struct TypeJob {
+    int svtype;
+    int64_t n_host;          // upper bound of the sorted-domain size
+    const uint32_t* n_dev;   // actual size when it is only known on the device (small types)
+    // INDEL: linear keys in sorted order
+    const uint32_t* keys32;
+    const uint64_t* keys64;
+    IndelView iv;
+    // DUP / INV / TRA: fully sorted, de-duplicated columns
+    SortedView sv;
+    ClusterParams cp;
+    uint32_t kslot_base;     // first global kept-cluster slot of this type
+    const uint32_t* kept_start;
+    uint32_t* big_list;
+    uint32_t* giant_list;
+    uint32_t big_cap, giant_cap;
+    char* giant_arena;
+};
+
+__device__ __forceinline__ int64_t job_n(const TypeJob& J) { return J.n_dev ? (int64_t)*J.n_dev : J.n_host; }
+
+// element i (> 0) belongs to the same chain cluster as element i-1
+__device__ __forceinline__ bool job_linked(const TypeJob& J, int64_t i) {
+    const int32_t bias = J.cp.bias;
+    switch (J.svtype) {
+        case CSV_DEL:
+        case CSV_INS:  // resolveINDEL.py:61,271 -- contigs are padded by > bias in the linear key
+            if (J.keys32) return (J.keys32[i] - J.keys32[i - 1]) <= (uint32_t)bias;
+            return (J.keys64[i] - J.keys64[i - 1]) <= (uint64_t)bias;
+        case CSV_DUP:  // resolveDUP.py:35
+            return J.sv.chrom[i] == J.sv.chrom[i - 1] && !(J.sv.a[i] - J.sv.a[i - 1] > bias);
+        case CSV_INV:  // resolveINV.py:56
+            return J.sv.chrom[i] == J.sv.chrom[i - 1] && J.sv.c[i] == J.sv.c[i - 1] && !(J.sv.a[i] - J.sv.a[i - 1] > bias) &&
+                   !(J.sv.b[i] - J.sv.b[i - 1] > bias);
+        default:       // TRA resolveTRA.py:41,65
+            return J.sv.chrom[i] == J.sv.chrom[i - 1] && J.sv.c[i] == J.sv.c[i - 1] && !(J.sv.a[i] - J.sv.a[i - 1] > bias);
+    }
+}
+
+// predicate of the segment step: i starts a chain cluster with at least min_support members
+struct HeadPred {
+    TypeJob J;
+    __device__ __forceinline__ bool operator()(int64_t i) const {
+        if (i > 0 && job_linked(J, i)) return false;
+        const int64_t n = job_n(J);
+        const int need = J.cp.min_support;
+        int cnt = 1;
+        int64_t j = i + 1;
+        while (cnt < need && j < n && job_linked(J, j)) { cnt++; j++; }
+        return cnt >= need;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// keys
+// ------------------------------------------------------------------------------------------
+struct ContigTab {
+    const uint64_t* off;   // linear offset of every contig (padded by > max bias), n+1 entries
+    const int64_t* len;
+    int32_t n;
+};
+
+template <typename K>
+__global__ void k_indel_keys(const int32_t* __restrict__ chrom, const int32_t* __restrict__ a, const int32_t* __restrict__ b,
+                             const int32_t* __restrict__ rid, int64_t n, int is_ins, ContigTab ct, K* __restrict__ keys,
+                             uint32_t* status) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t c = chrom[i];
+        uint32_t bad = 0;
+        K key = 0;
+        if (c < 0 || c >= ct.n) bad |= ST_BAD_CHROM;
+        else {
+            const int32_t raw = a[i];
+            const int64_t pos = is_ins ? (raw >> 1) : raw;
+            if (raw < 0 || pos > ct.len[c]) bad |= ST_BAD_POS;
+            else key = (K)(ct.off[c] + (uint64_t)pos);
+        }
+        if (rid[i] < 0 || b[i] < 0) bad |= ST_NEG_FIELD;
+        if (bad) atomicOr(status, bad);
+        keys[i] = key;
+    }
+}
+
+// small types: three sort keys per signature (name, second coordinate, primary)
+__global__ void k_other_keys(const int32_t* __restrict__ chrom, const int32_t* __restrict__ a, const int32_t* __restrict__ b,
+                             const int32_t* __restrict__ rid, const int32_t* __restrict__ c, int64_t n, int svtype, ContigTab ct,
+                             uint32_t* __restrict__ k_rid, uint32_t* __restrict__ k_b, uint64_t* __restrict__ k_prim,
+                             uint32_t* status) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t bad = 0;
+        const int32_t ch = chrom[i], ai = a[i], bi = b[i], ri = rid[i], ci = c ? c[i] : 0;
+        if (ch < 0 || ch >= ct.n) bad |= ST_BAD_CHROM;
+        if (ai < 0 || bi < 0 || ri < 0 || ci < 0) bad |= ST_NEG_FIELD;
+        if (svtype == CSV_TRA && (ci >> 2) >= ct.n) bad |= ST_BAD_CHROM;
+        if (svtype == CSV_INV && ci > 1) bad |= ST_NEG_FIELD;
+        if (bad) atomicOr(status, bad);
+        k_rid[i] = (uint32_t)ri;
+        k_b[i] = (uint32_t)bi;
+        // (chr, a) for DUP cuteSV:783; (chr, strand, bp1) for INV cuteSV:792; (chr1, chr2, type, pos1) for TRA :801
+        uint64_t hi = (uint64_t)(uint32_t)ch;
+        if (svtype == CSV_INV) hi = hi * 2 + (uint32_t)ci;
+        if (svtype == CSV_TRA) hi = (hi << 20) | (uint32_t)ci;   // chr2*4+type < 2^20
+        k_prim[i] = (hi << 31) | (uint32_t)ai;                     // a < 2^31
+    }
+}
+
+// keys_out[i] = src[perm[i]] (perm == nullptr: identity)
+template <typename K>
+__global__ void k_gather_keys(const K* __restrict__ src, const uint32_t* __restrict__ perm, int64_t n, K* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = src[perm ? perm[i] : (uint32_t)i];
+}
+
+// small types: exact-duplicate removal (cuteSV:958-969) in the final order
+struct DedupPred {
+    const int32_t *chrom, *a, *b, *rid, *c;
+    const uint32_t* perm;
+    __device__ __forceinline__ bool operator()(int64_t i) const {
+        if (i == 0) return true;
+        const uint32_t x = perm[i], y = perm[i - 1];
+        return !(chrom[x] == chrom[y] && a[x] == a[y] && b[x] == b[y] && rid[x] == rid[y] && (c ? c[x] == c[y] : true));
+    }
+};
+// U columns = input columns gathered through perm[sel[k]]
+__global__ void k_other_gather(const int32_t* __restrict__ chrom, const int32_t* __restrict__ a, const int32_t* __restrict__ b,
+                               const int32_t* __restrict__ rid, const int32_t* __restrict__ c, const uint32_t* __restrict__ perm,
+                               const uint32_t* __restrict__ sel, const uint32_t* n_sel, int32_t* u_chrom, int32_t* u_a, int32_t* u_b,
+                               int32_t* u_rid, int32_t* u_c) {
+    const int64_t n = *n_sel;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t x = perm[sel[k]];
+        u_chrom[k] = chrom[x]; u_a[k] = a[x]; u_b[k] = b[x]; u_rid[k] = rid[x]; u_c[k] = c ? c[x] : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// cluster kernels
+// ------------------------------------------------------------------------------------------
+template <class Team>
+__device__ __forceinline__ void run_cluster(Team tm, const TypeJob& J, int64_t s, int m, int M, char* arena, int64_t* red,
+                                            uint32_t kslot, const Emit& E) {
+    switch (J.svtype) {
+        case CSV_DEL:
+        case CSV_INS: indel_cluster(tm, J.iv, s, m, M, arena, red, J.cp, J.svtype, kslot, E); break;
+        case CSV_DUP: dup_cluster(tm, J.sv, s, m, M, arena, red, J.cp, kslot, E); break;
+        case CSV_INV: inv_cluster(tm, J.sv, s, m, M, arena, red, J.cp, kslot, E); break;
+        default: tra_cluster(tm, J.sv, s, m, M, arena, red, J.cp, kslot, E); break;
+    }
+}
+__device__ __forceinline__ int arena_per(const TypeJob& J) {
+    return (J.svtype == CSV_DEL || J.svtype == CSV_INS) ? INDEL_ARENA_PER : OTHER_ARENA_PER;
+}
+static constexpr int ARENA_PER_MAX = INDEL_ARENA_PER > OTHER_ARENA_PER ? INDEL_ARENA_PER : OTHER_ARENA_PER;
+
+// size of the chain cluster starting at s, counting at most `limit`+1 members (warp-cooperative)
+__device__ __forceinline__ int cluster_size_warp(const TypeJob& J, int64_t s, int64_t n, int limit) {
+    const int lane = threadIdx.x & 31;
+    int m = 1;
+    while (m <= limit) {
+        const int64_t i = s + m + lane;
+        const bool brk = (i >= n) || !job_linked(J, i);
+        const uint32_t mask = __ballot_sync(0xffffffffu, brk);
+        if (mask) { m += __ffs(mask) - 1; return m; }
+        m += 32;
+    }
+    return m;  // > limit
+}
+
+// one warp per kept cluster; clusters larger than WARP_M are deferred to the CTA kernel
+__global__ void __launch_bounds__(CL_THREADS) k_cluster_warp(TypeJob J, Emit E, Counters* ctr) {
+    extern __shared__ __align__(16) char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int WARPS = CL_THREADS / 32;
+    char* arena = smem + (size_t)warp * (WARP_M * ARENA_PER_MAX);
+    int64_t* red = (int64_t*)(smem + (size_t)WARPS * (WARP_M * ARENA_PER_MAX)) + warp * 40;
+    const int64_t n = job_n(J);
+    const uint32_t n_kept = ctr->n_kept[J.svtype];
+    CudaTeam<32> tm;
+    for (uint32_t k = blockIdx.x * WARPS + warp; k < n_kept; k += gridDim.x * WARPS) {
+        const int64_t s = J.kept_start[k];
+        const int m = cluster_size_warp(J, s, n, WARP_M);
+        if (m > WARP_M) {
+            if (lane == 0) {
+                const uint32_t o = atomicAdd(&ctr->n_big[J.svtype], 1u);
+                if (o < J.big_cap) J.big_list[o] = k; else atomicOr(&ctr->status, ST_LIST_OVERFLOW);
+            }
+            continue;
+        }
+        run_cluster(tm, J, s, m, pow2ceil(m), arena, red, J.kslot_base + k, E);
+        __syncwarp();
+    }
+}
+
+// size of the chain cluster starting at s (CTA-cooperative, exact)
+__device__ __forceinline__ int64_t cluster_size_block(const TypeJob& J, int64_t s, int64_t n, int64_t* red) {
+    CudaTeam<CL_THREADS> tm;
+    int64_t done = 1;
+    while (true) {
+        const int64_t i = s + done + threadIdx.x;
+        const int64_t cand = ((i >= n) || !job_linked(J, i)) ? (done + threadIdx.x) : INT64_MAX;
+        const int64_t first = team_min(tm, cand, red);
+        if (first != INT64_MAX) return first;
+        done += CL_THREADS;
+    }
+}
+
+// one CTA per deferred cluster; GIANT = arena in global scratch instead of shared memory
+template <bool GIANT>
+__global__ void __launch_bounds__(CL_THREADS) k_cluster_block(TypeJob J, Emit E, Counters* ctr) {
+    extern __shared__ __align__(16) char smem[];
+    __shared__ int64_t red[CL_THREADS + 8];
+    const int64_t n = job_n(J);
+    const uint32_t n_list = GIANT ? min(ctr->n_giant[J.svtype], J.giant_cap) : min(ctr->n_big[J.svtype], J.big_cap);
+    const uint32_t* list = GIANT ? J.giant_list : J.big_list;
+    CudaTeam<CL_THREADS> tm;
+    for (uint32_t q = blockIdx.x; q < n_list; q += gridDim.x) {
+        const uint32_t k = list[q];
+        const int64_t s = J.kept_start[k];
+        const int64_t m = cluster_size_block(J, s, n, red);
+        if (!GIANT && m > BLOCK_M) {
+            if (threadIdx.x == 0) {
+                const uint32_t o = atomicAdd(&ctr->n_giant[J.svtype], 1u);
+                if (o < J.giant_cap) J.giant_list[o] = k; else atomicOr(&ctr->status, ST_LIST_OVERFLOW);
+            }
+            __syncthreads();
+            continue;
+        }
+        const int M = pow2ceil((int)m);
+        // global scratch: clusters are disjoint ranges of the sorted order and M <= 2m
+        char* arena = GIANT ? (J.giant_arena + (size_t)(2 * s) * ARENA_PER_MAX) : smem;
+        run_cluster(tm, J, s, (int)m, M, arena, red, J.kslot_base + k, E);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// order: final position = (exclusive scan of per-cluster counts)[kslot] + emission rank
+// ------------------------------------------------------------------------------------------
+__global__ void k_permute(const csv_cand* __restrict__ tmp, const uint32_t* __restrict__ base, const Counters* ctr, uint32_t cap,
+                          csv_cand* __restrict__ out) {
+    const uint32_t n = min(ctr->n_cand, cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        csv_cand c = tmp[i];
+        const uint32_t dst = base[c.cluster] + (uint32_t)c.reserved[0];
+        c.reserved[0] = 0;
+        if (dst < cap) out[dst] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// genotype
+// ------------------------------------------------------------------------------------------
+struct GenoJob {
+    csv_cand* cand;           // final order
+    csv_geno* geno;
+    const int32_t* names;
+    const Counters* ctr;
+    uint32_t cap_cand;
+    ContigTab ct;
+    GtParams gp;
+    int shift;
+    uint32_t n_bins;
+    uint32_t* bin_start;      // n_bins + 1 (counts, then exclusive offsets)
+    uint32_t* bin_fill;       // n_bins
+    uint32_t* win_list;       // cand*2 + which, grouped by bin
+    uint32_t win_cap;
+    uint32_t* dr;             // per candidate
+    uint8_t* has_rows;        // per contig: reads table has rows (call_gt's `chr not in sigs_index["reads"]`)
+    const csv_geno* gl_table;
+    int genotype;
+};
+
+__device__ __forceinline__ uint32_t window_bin(const GenoJob& G, const csv_cand& c, int which) {
+    int64_t s, e;
+    window_of(c, which, G.gp, &s, &e);
+    return (uint32_t)((G.ct.off[c.chrom] + (uint64_t)s) >> G.shift);
+}
+
+// pass 0: count windows per bin; pass 1: scatter them (bin_start already scanned)
+template <int PASS>
+__global__ void k_windows(GenoJob G) {
+    const uint32_t n = min(G.ctr->n_cand, G.cap_cand);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const csv_cand c = G.cand[i];
+        const int nw = n_windows_of(c);
+        for (int w = 0; w < nw; w++) {
+            uint32_t b = window_bin(G, c, w);
+            if (b >= G.n_bins) b = G.n_bins - 1;
+            if (PASS == 0) atomicAdd(&G.bin_start[b], 1u);
+            else {
+                const uint32_t o = G.bin_start[b] + atomicAdd(&G.bin_fill[b], 1u);
+                if (o < G.win_cap) G.win_list[o] = i * 2u + (uint32_t)w;
+            }
+        }
+        if (PASS == 0) G.dr[i] = 0;
+    }
+}
+
+// ONE streaming pass over the reads table (replaces overlap_cover's event sort + sweep,
+// cuteSV_genotype.py:95-159): a primary read covers window [s,e] iff start <= s and end >= e;
+// it can only cover windows whose s lies in a bin it overlaps.
+__global__ void k_reads_pass(GenoJob G, const int32_t* __restrict__ r_chrom, const int32_t* __restrict__ r_start,
+                             const int32_t* __restrict__ r_end, const int32_t* __restrict__ r_id, const uint8_t* __restrict__ r_prim,
+                             int64_t n_reads, uint32_t* status) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t ch = r_chrom[r];
+        if (ch < 0 || ch >= G.ct.n) { atomicOr(status, ST_BAD_CHROM); continue; }
+        if (!G.has_rows[ch]) G.has_rows[ch] = 1;
+        if (!r_prim[r]) continue;
+        const uint64_t off = G.ct.off[ch];
+        const uint64_t RS = off + (uint64_t)(uint32_t)r_start[r], RE = off + (uint64_t)(uint32_t)r_end[r];
+        uint32_t b0 = (uint32_t)(RS >> G.shift), b1 = (uint32_t)(RE >> G.shift);
+        if (b1 >= G.n_bins) b1 = G.n_bins - 1;
+        if (b0 > b1) continue;
+        uint32_t w = G.bin_start[b0];
+        const uint32_t we = G.bin_start[b1 + 1];
+        const int32_t rid = r_id[r];
+        for (; w < we; w++) {
+            const uint32_t ent = G.win_list[w];
+            const csv_cand c = G.cand[ent >> 1];
+            const uint64_t coff = G.ct.off[c.chrom];
+            int64_t s, e;
+            window_of(c, (int)(ent & 1u), G.gp, &s, &e);
+            if (!(RS <= coff + (uint64_t)s && RE >= coff + (uint64_t)e)) continue;
+            if (ent & 1u) {  // union of the two breakpoint covers (resolveDUP.py:155-157): count once
+                int64_t s0, e0;
+                window_of(c, 0, G.gp, &s0, &e0);
+                if (RS <= coff + (uint64_t)s0 && RE >= coff + (uint64_t)e0) continue;
+            }
+            bool sup = false;  // assign_gt: DR counts covering reads that are not supporting reads
+            const int32_t* nm = G.names + c.names_off;
+            for (int k = 0; k < c.names_cnt; k++)
+                if (nm[k] == rid) { sup = true; break; }
+            if (!sup) atomicAdd(&G.dr[ent >> 1], 1u);
+        }
+    }
+}
+
+__global__ void k_finalize(GenoJob G) {
+    const uint32_t n = min(G.ctr->n_cand, G.cap_cand);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        csv_cand c = G.cand[i];
+        csv_geno g;
+        g.dr = -1; g.dv = c.names_cnt; g.gt = -1; g.pl[0] = g.pl[1] = g.pl[2] = 0; g.gq = 0; g.status = 1; g.qual = 0.0;
+        if (G.genotype && n_windows_of(c) > 0) {
+            if (!G.has_rows[c.chrom]) {
+                c.flags |= CSV_F_NO_READS;
+                G.cand[i].flags = c.flags;
+            } else {
+                const int32_t dr = (int32_t)G.dr[i];
+                g = G.gl_table[gl_index(dr, c.names_cnt)];  // cal_GL(DR, DV) (cuteSV_genotype.py:171)
+                g.dr = dr; g.dv = c.names_cnt;
+            }
+        }
+        G.geno[i] = g;
+    }
+}
+
+// cal_GL for arbitrary (c0, c1) pairs: special cases + rescale on the device, libm part from the table
+__global__ void k_cal_gl(const int32_t* c0, const int32_t* c1, int64_t n, const csv_geno* gl_table, csv_geno* out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        csv_geno g = gl_table[gl_index(c0[i], c1[i])];
+        g.dr = c0[i]; g.dv = c1[i];
+        out[i] = g;
+    }
+}
+
+}  // namespace csv

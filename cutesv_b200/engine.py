@@ -1,0 +1,126 @@
+"""Engine: one csv_ctx (one GPU) driven from Python.  Host side of the drop-in boundary."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi, _lib
+
+
+class Engine(object):
+    """Owns a csv_ctx.  stream: optional cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
+
+    def __init__(self, device=0, stream=None, params=None, contig_lens=None):
+        self.L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(self.L.csv_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = int(device)
+        self.params = None
+        self._keep = None
+        self.set_params(params if params is not None else _abi.default_params())
+        if contig_lens is not None:
+            self.set_contigs(contig_lens)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.csv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params):
+        self.params = params
+        _lib.check(self.L.csv_set_params(self.h, C.byref(params)))
+
+    def set_contigs(self, lens):
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        self.n_contigs = len(lens)
+        _lib.check(self.L.csv_set_contigs(self.h, C.c_int32(len(lens)), lens.ctypes.data_as(C.POINTER(C.c_int64))))
+
+    def set_profiling(self, on):
+        _lib.check(self.L.csv_set_profiling(self.h, int(bool(on))))
+
+    # -- device-resident path (bench `value`): upload once, cluster many times --
+    def upload(self, sigs, reads):
+        keep = []
+        for t, name in enumerate(_abi.TYPE_NAMES):
+            s, k = _abi.make_sig_cols(sigs.get(name))
+            keep.append(k)
+            _lib.check(self.L.csv_upload_sigs(self.h, t, C.byref(s)))
+        r, rk = _abi.make_reads_cols(reads)
+        keep.append(rk)
+        _lib.check(self.L.csv_upload_reads(self.h, C.byref(r)))
+        self._keep = keep  # host buffers must outlive the async copies
+
+    def cluster_device(self, type_mask=0x1F):
+        _lib.check(self.L.csv_cluster(self.h, C.c_uint32(type_mask)))
+
+    def counts(self):
+        nc, nn = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.L.csv_result_counts(self.h, C.byref(nc), C.byref(nn)))
+        return nc.value, nn.value
+
+    def fetch(self):
+        nc, nn = self.counts()
+        cands = np.zeros(max(nc, 1), dtype=_abi.CAND_DTYPE)
+        genos = np.zeros(max(nc, 1), dtype=_abi.GENO_DTYPE)
+        names = np.zeros(max(nn, 1), dtype=np.int32)
+        _lib.check(self.L.csv_fetch(self.h, cands.ctypes.data_as(C.c_void_p), genos.ctypes.data_as(C.c_void_p), C.c_int64(len(cands)),
+                                    _abi.ptr(names), C.c_int64(len(names))))
+        return cands[:nc], genos[:nc], names[:nn]
+
+    # -- the reference-facing one-shot call: host columns in, host rows out --
+    def cluster(self, sigs, reads, type_mask=0x1F, out=None):
+        """sigs: {type_name: dict(chrom,a,b,read_id[,c])}; reads: dict(chrom,start,end,read_id,is_primary).
+        Returns (cands, genos, names) numpy arrays in the reference's emission order."""
+        arr = (_abi.csv_sig_cols * _abi.CSV_NTYPES)()
+        keep = []
+        total = 0
+        for t, name in enumerate(_abi.TYPE_NAMES):
+            s, k = _abi.make_sig_cols(sigs.get(name))
+            arr[t] = s
+            keep.append(k)
+            total += s.n
+        r, rk = _abi.make_reads_cols(reads)
+        if out is None:
+            cap_c = max(total // max(min(self.params.min_support_allele, self.params.min_support), 1) + 16, 16)
+            cap_n = total + 16
+            cands = np.zeros(cap_c, dtype=_abi.CAND_DTYPE)
+            genos = np.zeros(cap_c, dtype=_abi.GENO_DTYPE)
+            names = np.zeros(cap_n, dtype=np.int32)
+        else:
+            cands, genos, names = out
+        nc, nn = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.L.csv_cluster_host(self.h, arr, C.byref(r), C.c_uint32(type_mask), cands.ctypes.data_as(C.c_void_p),
+                                           genos.ctypes.data_as(C.c_void_p), C.c_int64(len(cands)), _abi.ptr(names),
+                                           C.c_int64(len(names)), C.byref(nc), C.byref(nn)))
+        return cands[:nc.value], genos[:nc.value], names[:nn.value]
+
+    def cal_gl(self, c0, c1):
+        c0 = np.ascontiguousarray(c0, dtype=np.int32)
+        c1 = np.ascontiguousarray(c1, dtype=np.int32)
+        out = np.zeros(len(c0), dtype=_abi.GENO_DTYPE)
+        _lib.check(self.L.csv_cal_gl(self.h, _abi.ptr(c0), _abi.ptr(c1), C.c_int64(len(c0)), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def stage_ms(self):
+        ms = (C.c_float * _abi.CSV_ST_COUNT)()
+        _lib.check(self.L.csv_stage_ms(self.h, ms))
+        return {name: float(ms[i]) for i, name in enumerate(_abi.STAGES)}
+
+    def sort_probe(self):
+        ms, b, n = C.c_float(0), C.c_int64(0), C.c_int32(0)
+        _lib.check(self.L.csv_sort_probe(self.h, C.byref(ms), C.byref(b), C.byref(n)))
+        return dict(ms=float(ms.value), bytes=int(b.value), launches=int(n.value))
+
+    def launch_count(self):
+        return int(self.L.csv_launch_count(self.h))
+
+    def device_ptrs(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(self.L.csv_result_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
