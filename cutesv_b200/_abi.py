@@ -1,7 +1,7 @@
 """ctypes / numpy mirrors of include/cutesv_b200.h (struct layouts only, no library loading).
 
 Shared by the product binding (cutesv_b200/_lib.py) and by the test-only oracle binding
-(oracle/oracle_lib.py); the header is the single source of truth for the layouts.
+(the oracle wrapper under oracle/); the header is the single source of truth for the layouts.
 """
 import ctypes as C
 
