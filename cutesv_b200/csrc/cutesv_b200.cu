@@ -103,7 +103,7 @@ struct csv_ctx {
     uint32_t cap_cand = 0, cap_names = 0;
     Counters* h_counters = nullptr;  // pinned
     // genotype
-    DBuf bin_start, bin_fill, win_list, dr, has_rows, gl_table, pow_half;
+    DBuf bin_start, bin_fill, bin_bits, win_list, dr, has_rows, gl_table, pow_half, pairs;
     uint32_t pow_n = 0;
     // state
     bool ran = false, counts_valid = false;
@@ -252,7 +252,7 @@ extern "C" int csv_destroy(csv_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DBuf* all[] = {&c->d_off, &c->d_len, &c->r_chrom, &c->r_start, &c->r_end, &c->r_id, &c->r_prim, &c->keys_a, &c->keys_b,
                    &c->vals_a, &c->vals_b, &c->hist, &c->lb_status, &c->tickets, &c->big_list, &c->giant_list, &c->giant_arena,
-                   &c->cnt, &c->cand_tmp, &c->cand, &c->geno, &c->names, &c->counters, &c->bin_start, &c->bin_fill, &c->win_list,
+                   &c->cnt, &c->cand_tmp, &c->cand, &c->geno, &c->names, &c->counters, &c->bin_start, &c->bin_fill, &c->bin_bits, &c->pairs, &c->win_list,
                    &c->dr, &c->has_rows, &c->gl_table, &c->pow_half, &c->small.k_rid, &c->small.k_b, &c->small.k_prim,
                    &c->small.perm_a, &c->small.perm_b, &c->small.sel, &c->small.u_chrom, &c->small.u_a, &c->small.u_b,
                    &c->small.u_rid, &c->small.u_c};
@@ -465,12 +465,19 @@ static int run_segment_and_cluster(csv_ctx* c, TypeJob& J, int t, uint32_t kslot
     J.big_list = c->big_list.as<uint32_t>();
     J.giant_list = c->giant_list.as<uint32_t>();
     J.giant_arena = c->giant_arena.as<char>();
+    J.big_cap = (uint32_t)(c->big_list.cap / 4);
+    J.giant_cap = (uint32_t)(c->giant_list.cap / 4);
     TileSync ts;
     int rc = make_sync(c, (size_t)(J.n_host / SEL_TILE + 2), &ts);
     if (rc) return rc;
-    HeadPred hp{J};
-    LAUNCH(c, (k_select<HeadPred>), grid_for(c, J.n_host, SEL_TILE, 4), SEL_THREADS, 0, hp, J.n_host, J.n_dev,
-           c->kept[t].as<uint32_t>(), c->kept_cap[t], &ctr->n_kept[t], ts, &ctr->status, (uint32_t)ST_LIST_OVERFLOW);
+    if ((J.cp.min_support + 31) / 32 + 1 <= HEAD_MAX_NEED_WORDS) {
+        LAUNCH(c, k_select_heads, grid_for(c, J.n_host, SEL_TILE, 4), SEL_THREADS, 0, J, c->kept[t].as<uint32_t>(), c->kept_cap[t],
+               &ctr->n_kept[t], ts, &ctr->status, (uint32_t)ST_LIST_OVERFLOW);
+    } else {
+        HeadPred hp{J};
+        LAUNCH(c, (k_select<HeadPred>), grid_for(c, J.n_host, SEL_TILE, 4), SEL_THREADS, 0, hp, J.n_host, J.n_dev,
+               c->kept[t].as<uint32_t>(), c->kept_cap[t], &ctr->n_kept[t], ts, &ctr->status, (uint32_t)ST_LIST_OVERFLOW);
+    }
     stage_end(c, CSV_ST_SEGMENT);
     // ---- cluster ----
     stage_begin(c, CSV_ST_CLUSTER);
@@ -665,7 +672,7 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
         memset(&G, 0, sizeof(G));
         const uint64_t total = c->contig_off[c->n_contigs];
         int shift = 10;
-        while ((total >> shift) > (1u << 18)) shift++;
+        while ((total >> shift) > (1u << 20)) shift++;
         G.cand = c->cand.as<csv_cand>(); G.geno = c->geno.as<csv_geno>(); G.names = c->names.as<int32_t>(); G.ctr = ctr;
         G.cap_cand = c->cap_cand;
         G.ct = ContigTab{c->d_off.as<uint64_t>(), c->d_len.as<int64_t>(), c->n_contigs};
@@ -674,7 +681,8 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
         G.n_bins = (uint32_t)(total >> shift) + 2;
         CU(c->bin_start.ensure(((size_t)G.n_bins + 1) * 4));
         CU(c->bin_fill.ensure((size_t)G.n_bins * 4));
-        G.bin_start = c->bin_start.as<uint32_t>(); G.bin_fill = c->bin_fill.as<uint32_t>();
+        CU(c->bin_bits.ensure(((size_t)G.n_bins / 32 + 2) * 4));
+        G.bin_start = c->bin_start.as<uint32_t>(); G.bin_fill = c->bin_fill.as<uint32_t>(); G.bin_bits = c->bin_bits.as<uint32_t>();
         G.win_list = c->win_list.as<uint32_t>(); G.win_cap = c->cap_cand * 2;
         G.dr = c->dr.as<uint32_t>(); G.has_rows = c->has_rows.as<uint8_t>();
         G.gl_table = c->gl_table.as<csv_geno>();
@@ -682,6 +690,7 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
         if (c->P.genotype) {
             CU(cudaMemsetAsync(G.bin_start, 0, ((size_t)G.n_bins + 1) * 4, c->stream));
             CU(cudaMemsetAsync(G.bin_fill, 0, (size_t)G.n_bins * 4, c->stream));
+            CU(cudaMemsetAsync(G.bin_bits, 0, ((size_t)G.n_bins / 32 + 2) * 4, c->stream));
             CU(cudaMemsetAsync(G.has_rows, 0, (size_t)c->n_contigs, c->stream));
             LAUNCH(c, (k_windows<0>), grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
             TileSync ts;
@@ -690,9 +699,17 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
             LAUNCH(c, k_scan_excl, grid_for(c, G.n_bins + 1, SEL_TILE, 2), SEL_THREADS, 0, G.bin_start, (int64_t)G.n_bins + 1,
                    (const uint32_t*)nullptr, (uint32_t*)nullptr, ts);
             LAUNCH(c, (k_windows<1>), grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
-            if (c->n_reads > 0)
-                LAUNCH(c, k_reads_pass, grid_for(c, c->n_reads, 256, 16), 256, 0, G, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+            if (c->n_reads > 0) {
+                PairBuf PB;
+                PB.cap = (uint32_t)std::min<int64_t>(2 * c->n_reads + (1 << 20), (int64_t)1 << 30);
+                CU(c->pairs.ensure((size_t)PB.cap * sizeof(uint2)));
+                PB.pairs = c->pairs.as<uint2>();
+                PB.count = &ctr->n_windows;
+                LAUNCH(c, k_reads_pass, grid_for(c, c->n_reads, 256, 8), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
                        c->r_end.as<int32_t>(), c->r_id.as<int32_t>(), c->r_prim.as<uint8_t>(), c->n_reads, &ctr->status);
+                LAUNCH(c, k_pairs_test, c->n_sm * 8, 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                       c->r_end.as<int32_t>(), c->r_id.as<int32_t>());
+            }
         }
         LAUNCH(c, k_finalize, grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
     }

@@ -18,26 +18,49 @@ static constexpr uint32_t LB_MASK = (1u << 30) - 1;
 // look-back gets a fresh generation number from the host, so the status buffer never has to be
 // cleared: words of older generations simply read as "not published yet".
 __device__ __forceinline__ uint64_t lb_word(uint32_t gen, uint32_t flag_value) { return ((uint64_t)gen << 32) | flag_value; }
-__device__ __forceinline__ uint32_t lb_wait(volatile uint64_t* p, uint32_t gen) {
+// gpu-scope relaxed accesses: coherent at L2, no L1 caching, cheaper than volatile (.sys)
+__device__ __forceinline__ uint64_t lb_load(const uint64_t* p) {
     uint64_t v;
-    do { v = *p; } while ((uint32_t)(v >> 32) != gen || (((uint32_t)v) >> 30) == 0);
-    return (uint32_t)v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
+__device__ __forceinline__ void lb_store(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool lb_ready(uint64_t v, uint32_t gen) { return (uint32_t)(v >> 32) == gen && (((uint32_t)v) >> 30) != 0; }
 
-// One thread publishes `local` for `tile` and returns the exclusive prefix over tiles < tile.
-__device__ __forceinline__ uint32_t lookback_exclusive(volatile uint64_t* status, uint32_t gen, int tile, uint32_t local) {
+// Warp-cooperative look-back (all 32 lanes of ONE warp call it): publishes `local` for `tile`
+// and returns the exclusive prefix over tiles < tile to every lane.  32 predecessors are
+// inspected per step, so a wave of W concurrently running tiles costs W/32 dependent L2 round
+// trips instead of W.
+__device__ __forceinline__ uint32_t lookback_exclusive_warp(uint64_t* status, uint32_t gen, int tile, uint32_t local) {
+    const int lane = threadIdx.x & 31;
     if (tile == 0) {
-        status[0] = lb_word(gen, local | LB_INCL);
+        if (lane == 0) lb_store(status, lb_word(gen, local | LB_INCL));
         return 0;
     }
-    status[tile] = lb_word(gen, local | LB_LOCAL);
+    if (lane == 0) lb_store(status + tile, lb_word(gen, local | LB_LOCAL));
     uint32_t excl = 0;
-    for (int p = tile - 1; p >= 0; p--) {
-        const uint32_t v = lb_wait(status + p, gen);
-        excl += v & LB_MASK;
-        if ((v >> 30) == 2) break;
+    int p = tile - 1;
+    while (true) {
+        const int q = p - lane;
+        const uint64_t v = q >= 0 ? lb_load(status + q) : lb_word(gen, LB_INCL);
+        const uint32_t w = (uint32_t)v;
+        const bool ready = lb_ready(v, gen);
+        const uint32_t nr = __ballot_sync(0xffffffffu, !ready);
+        const uint32_t inc = __ballot_sync(0xffffffffu, ready && (w >> 30) == 2);
+        const int first_nr = nr ? __ffs(nr) - 1 : 32;
+        const int first_inc = inc ? __ffs(inc) - 1 : 32;
+        const bool done = first_inc < first_nr;
+        const int upto = done ? first_inc + 1 : first_nr;  // lanes [0, upto) are consumed
+        uint32_t contrib = lane < upto ? (w & LB_MASK) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (done) break;
+        p -= upto;  // upto == 0: the nearest predecessor has not published yet -> poll again
     }
-    status[tile] = lb_word(gen, (excl + local) | LB_INCL);
+    if (lane == 0) lb_store(status + tile, lb_word(gen, (excl + local) | LB_INCL));
     return excl;
 }
 
@@ -105,9 +128,12 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(Pred pred, int64_t n_hos
         }
         uint32_t total;
         const uint32_t local = block_excl_scan_256(cnt, s_warp, &total);
-        if (threadIdx.x == 0) {
-            s_excl = lookback_exclusive(ts.status, ts.gen, (int)tile, total);
-            if (base + SEL_TILE >= n) *out_count = s_excl + total;
+        if (threadIdx.x < 32) {
+            const uint32_t ex = lookback_exclusive_warp(ts.status, ts.gen, (int)tile, total);
+            if (threadIdx.x == 0) {
+                s_excl = ex;
+                if (base + SEL_TILE >= n) *out_count = ex + total;
+            }
         }
         __syncthreads();
         uint32_t o = s_excl + local;
@@ -144,9 +170,12 @@ __global__ void __launch_bounds__(SEL_THREADS) k_scan_excl(uint32_t* arr, int64_
         }
         uint32_t total;
         const uint32_t local = block_excl_scan_256(cnt, s_warp, &total);
-        if (threadIdx.x == 0) {
-            s_excl = lookback_exclusive(ts.status, ts.gen, (int)tile, total);
-            if (total_out && base + SEL_TILE >= n) *total_out = s_excl + total;
+        if (threadIdx.x < 32) {
+            const uint32_t ex = lookback_exclusive_warp(ts.status, ts.gen, (int)tile, total);
+            if (threadIdx.x == 0) {
+                s_excl = ex;
+                if (total_out && base + SEL_TILE >= n) *total_out = ex + total;
+            }
         }
         __syncthreads();
         uint32_t run = s_excl + local;

@@ -72,6 +72,87 @@ struct HeadPred {
     }
 };
 
+// Segment step, specialised: the chain-linkage votes of a 2048-element tile are taken with
+// coalesced loads and kept as a bit mask in shared memory (one __ballot_sync per 32 elements);
+// "i starts a cluster of >= min_support members" is then a bit test: link[i] == 0 and
+// link[i+1 .. i+min_support-1] all 1.  Ordered compaction as in k_select.
+static constexpr int HEAD_MAX_NEED_WORDS = 64;  // supports min_support up to ~2000 via the mask; above -> generic path
+__global__ void __launch_bounds__(SEL_THREADS) k_select_heads(TypeJob J, uint32_t* out, uint32_t out_cap, uint32_t* out_count,
+                                                              TileSync ts, uint32_t* status_word, uint32_t overflow_bit) {
+    constexpr int WORDS = SEL_TILE / 32;
+    __shared__ uint32_t s_link[WORDS + HEAD_MAX_NEED_WORDS + 2];
+    __shared__ uint32_t s_warp[9];
+    __shared__ uint32_t s_tile, s_excl;
+    const int64_t n = job_n(J);
+    const int need = J.cp.min_support;
+    const int halo_words = (need + 31) / 32 + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ts.ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        const int64_t base = (int64_t)tile * SEL_TILE;
+        if (base >= n) break;
+        // link bits for [base, base + SEL_TILE + 32*halo_words): votes are evaluated in batches
+        // of 8 words per warp so that the key loads of a batch are all in flight together
+        for (int w0 = warp; w0 < WORDS + halo_words; w0 += 8 * (SEL_THREADS / 32)) {
+            bool l[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int w = w0 + u * (SEL_THREADS / 32);
+                const int64_t i = base + (int64_t)w * 32 + lane;
+                l[u] = (w < WORDS + halo_words && i > 0 && i < n) ? job_linked(J, i) : false;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int w = w0 + u * (SEL_THREADS / 32);
+                const uint32_t m = __ballot_sync(0xffffffffu, l[u]);
+                if (lane == 0 && w < WORDS + halo_words) s_link[w] = m;
+            }
+        }
+        __syncthreads();
+        const int p0 = threadIdx.x * SEL_ITEMS;
+        uint32_t flags = 0, cnt = 0;
+#pragma unroll
+        for (int j = 0; j < SEL_ITEMS; j++) {
+            const int p = p0 + j;
+            if (base + p >= n) continue;
+            if (s_link[p >> 5] >> (p & 31) & 1u) continue;   // chained to its predecessor: not a head
+            // bits p+1 .. p+need-1 must all be set
+            int remaining = need - 1, q = p + 1;
+            bool ok = true;
+            while (remaining > 0) {
+                const int wi = q >> 5, bo = q & 31;
+                const int take = min(32 - bo, remaining);
+                const uint32_t mask = (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) << bo;
+                if ((s_link[wi] & mask) != mask) { ok = false; break; }
+                q += take; remaining -= take;
+            }
+            if (ok) { flags |= 1u << j; cnt++; }
+        }
+        uint32_t total;
+        const uint32_t local = block_excl_scan_256(cnt, s_warp, &total);
+        if (threadIdx.x < 32) {
+            const uint32_t ex = lookback_exclusive_warp(ts.status, ts.gen, (int)tile, total);
+            if (threadIdx.x == 0) {
+                s_excl = ex;
+                if (base + SEL_TILE >= n) *out_count = ex + total;
+            }
+        }
+        __syncthreads();
+        uint32_t o = s_excl + local;
+#pragma unroll
+        for (int j = 0; j < SEL_ITEMS; j++) {
+            if (flags >> j & 1u) {
+                if (o < out_cap) out[o] = (uint32_t)(base + p0 + j);
+                else atomicOr(status_word, overflow_bit);
+                o++;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // keys
 // ------------------------------------------------------------------------------------------
@@ -283,6 +364,7 @@ struct GenoJob {
     uint32_t n_bins;
     uint32_t* bin_start;      // n_bins + 1 (counts, then exclusive offsets)
     uint32_t* bin_fill;       // n_bins
+    uint32_t* bin_bits;       // n_bins/32 + 1: bin holds at least one window (small, stays in L1)
     uint32_t* win_list;       // cand*2 + which, grouped by bin
     uint32_t win_cap;
     uint32_t* dr;             // per candidate
@@ -307,7 +389,7 @@ __global__ void k_windows(GenoJob G) {
         for (int w = 0; w < nw; w++) {
             uint32_t b = window_bin(G, c, w);
             if (b >= G.n_bins) b = G.n_bins - 1;
-            if (PASS == 0) atomicAdd(&G.bin_start[b], 1u);
+            if (PASS == 0) { atomicAdd(&G.bin_start[b], 1u); atomicOr(&G.bin_bits[b >> 5], 1u << (b & 31)); }
             else {
                 const uint32_t o = G.bin_start[b] + atomicAdd(&G.bin_fill[b], 1u);
                 if (o < G.win_cap) G.win_list[o] = i * 2u + (uint32_t)w;
@@ -317,43 +399,101 @@ __global__ void k_windows(GenoJob G) {
     }
 }
 
+// One (read, window) test of assign_gt / overlap_cover: a primary read covers window [s,e] iff
+// start <= s and end >= e (cuteSV_genotype.py:100-138); DR counts covering reads that are not
+// supporting reads (:161-173).  RS/RE are linear coordinates.
+__device__ __forceinline__ void test_pair(const GenoJob& G, uint64_t RS, uint64_t RE, int32_t rid, uint32_t w) {
+    const uint32_t ent = G.win_list[w];
+    const csv_cand c = G.cand[ent >> 1];
+    const uint64_t coff = G.ct.off[c.chrom];
+    int64_t s, e;
+    window_of(c, (int)(ent & 1u), G.gp, &s, &e);
+    if (!(RS <= coff + (uint64_t)s && RE >= coff + (uint64_t)e)) return;
+    if (ent & 1u) {  // union of the two breakpoint covers (resolveDUP.py:155-157): count once
+        int64_t s0, e0;
+        window_of(c, 0, G.gp, &s0, &e0);
+        if (RS <= coff + (uint64_t)s0 && RE >= coff + (uint64_t)e0) return;
+    }
+    const int32_t* nm = G.names + c.names_off;
+    for (int k = 0; k < c.names_cnt; k++)
+        if (nm[k] == rid) return;
+    atomicAdd(&G.dr[ent >> 1], 1u);
+}
+
 // ONE streaming pass over the reads table (replaces overlap_cover's event sort + sweep,
-// cuteSV_genotype.py:95-159): a primary read covers window [s,e] iff start <= s and end >= e;
-// it can only cover windows whose s lies in a bin it overlaps.
-__global__ void k_reads_pass(GenoJob G, const int32_t* __restrict__ r_chrom, const int32_t* __restrict__ r_start,
-                             const int32_t* __restrict__ r_end, const int32_t* __restrict__ r_id, const uint8_t* __restrict__ r_prim,
-                             int64_t n_reads, uint32_t* status) {
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t ch = r_chrom[r];
-        if (ch < 0 || ch >= G.ct.n) { atomicOr(status, ST_BAD_CHROM); continue; }
-        if (!G.has_rows[ch]) G.has_rows[ch] = 1;
-        if (!r_prim[r]) continue;
-        const uint64_t off = G.ct.off[ch];
-        const uint64_t RS = off + (uint64_t)(uint32_t)r_start[r], RE = off + (uint64_t)(uint32_t)r_end[r];
-        uint32_t b0 = (uint32_t)(RS >> G.shift), b1 = (uint32_t)(RE >> G.shift);
-        if (b1 >= G.n_bins) b1 = G.n_bins - 1;
-        if (b0 > b1) continue;
-        uint32_t w = G.bin_start[b0];
-        const uint32_t we = G.bin_start[b1 + 1];
-        const int32_t rid = r_id[r];
-        for (; w < we; w++) {
-            const uint32_t ent = G.win_list[w];
-            const csv_cand c = G.cand[ent >> 1];
-            const uint64_t coff = G.ct.off[c.chrom];
-            int64_t s, e;
-            window_of(c, (int)(ent & 1u), G.gp, &s, &e);
-            if (!(RS <= coff + (uint64_t)s && RE >= coff + (uint64_t)e)) continue;
-            if (ent & 1u) {  // union of the two breakpoint covers (resolveDUP.py:155-157): count once
-                int64_t s0, e0;
-                window_of(c, 0, G.gp, &s0, &e0);
-                if (RS <= coff + (uint64_t)s0 && RE >= coff + (uint64_t)e0) continue;
+// cuteSV_genotype.py:95-159).  A read can only cover windows whose start lies in a bin it
+// overlaps; most reads overlap no occupied bin (bit test on an L1-resident map).  The few
+// (read, window) pairs that remain are compacted (warp-aggregated append) and tested by a second,
+// dense kernel so that the streaming pass keeps all 32 lanes busy.
+struct PairBuf { uint2* pairs; uint32_t cap; uint32_t* count; };
+
+__global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const int32_t* __restrict__ r_chrom,
+                                                    const int32_t* __restrict__ r_start, const int32_t* __restrict__ r_end,
+                                                    const int32_t* __restrict__ r_id, const uint8_t* __restrict__ r_prim,
+                                                    int64_t n_reads, uint32_t* status) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = (n_reads + 31) / 32 * 32;   // whole warps iterate together
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_round; r += stride) {
+        uint32_t w = 0, cnt = 0;
+        uint64_t RS = 0, RE = 0;
+        if (r < n_reads) {
+            const int32_t ch = r_chrom[r];
+            if (ch < 0 || ch >= G.ct.n) atomicOr(status, ST_BAD_CHROM);
+            else {
+                if (!G.has_rows[ch]) G.has_rows[ch] = 1;
+                if (r_prim[r]) {
+                    const uint64_t off = G.ct.off[ch];
+                    RS = off + (uint64_t)(uint32_t)r_start[r];
+                    RE = off + (uint64_t)(uint32_t)r_end[r];
+                    const uint32_t b0 = (uint32_t)(RS >> G.shift);
+                    uint32_t b1 = (uint32_t)(RE >> G.shift);
+                    if (b1 >= G.n_bins) b1 = G.n_bins - 1;
+                    if (b0 <= b1) {
+                        bool any = false;
+                        for (uint32_t wi = b0 >> 5; wi <= (b1 >> 5) && !any; wi++) {
+                            uint32_t m = __ldg(&G.bin_bits[wi]);
+                            if (wi == (b0 >> 5)) m &= 0xffffffffu << (b0 & 31);
+                            if (wi == (b1 >> 5)) m &= 0xffffffffu >> (31 - (b1 & 31));
+                            any = m != 0;
+                        }
+                        if (any) { w = G.bin_start[b0]; cnt = G.bin_start[b1 + 1] - w; }
+                    }
+                }
             }
-            bool sup = false;  // assign_gt: DR counts covering reads that are not supporting reads
-            const int32_t* nm = G.names + c.names_off;
-            for (int k = 0; k < c.names_cnt; k++)
-                if (nm[k] == rid) { sup = true; break; }
-            if (!sup) atomicAdd(&G.dr[ent >> 1], 1u);
         }
+        // warp-aggregated append of (read, window slot) pairs
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(PB.count, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        uint32_t o = base + incl - cnt;
+        if (cnt) {
+            if ((uint64_t)o + cnt <= PB.cap) {
+                for (uint32_t k = 0; k < cnt; k++) PB.pairs[o + k] = make_uint2((uint32_t)r, w + k);
+            } else {  // pair buffer full: test inline (correct, just slower)
+                const int32_t rid = r_id[r];
+                for (uint32_t k = 0; k < cnt; k++) test_pair(G, RS, RE, rid, w + k);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pairs_test(GenoJob G, PairBuf PB, const int32_t* __restrict__ r_chrom,
+                                                    const int32_t* __restrict__ r_start, const int32_t* __restrict__ r_end,
+                                                    const int32_t* __restrict__ r_id) {
+    const uint32_t n = min(*PB.count, PB.cap);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const uint2 pr = PB.pairs[p];
+        const uint64_t off = G.ct.off[r_chrom[pr.x]];
+        test_pair(G, off + (uint64_t)(uint32_t)r_start[pr.x], off + (uint64_t)(uint32_t)r_end[pr.x], r_id[pr.x], pr.y);
     }
 }
 

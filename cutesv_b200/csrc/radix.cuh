@@ -15,6 +15,29 @@ static constexpr int RS_THREADS = 256;
 static constexpr int RS_WARPS = RS_THREADS / 32;
 static constexpr int RS_MAX_PASSES = 8;
 
+// Peer mask of the lanes holding the same 8-bit digit, built from 8 warp votes.  MATCH.ANY is a
+// long-latency, low-throughput instruction on sm_100 (ncu: ~45 % of all stall samples of the
+// first version sat on its result); eight VOTE.BALLOTs pipeline and cost less.
+__device__ __forceinline__ uint32_t match_digit8(uint32_t d) {
+    uint32_t ret = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        uint32_t mask;
+        asm volatile(
+            "{\n"
+            "  .reg .pred p;\n"
+            "  and.b32 %0, %1, %2;\n"
+            "  setp.ne.u32 p, %0, 0;\n"
+            "  vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+            "  @!p not.b32 %0, %0;\n"
+            "}\n"
+            : "=r"(mask)
+            : "r"(d), "r"(1u << b));
+        ret &= mask;
+    }
+    return ret;
+}
+
 template <typename K> struct RsTraits;
 template <> struct RsTraits<uint32_t> { static constexpr int ITEMS = 16; };
 template <> struct RsTraits<uint64_t> { static constexpr int ITEMS = 12; };
@@ -52,10 +75,10 @@ __global__ void __launch_bounds__(256) k_rs_hist_scan(uint32_t* hist, int passes
 // One pass.  status: n_tiles * 256 generation-tagged words (never cleared), ticket: 1 word (zeroed).
 // IOTA: the payload of element i is i itself (first pass; saves one column read).
 template <typename K, bool IOTA>
-__global__ void __launch_bounds__(RS_THREADS) k_rs_onesweep(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+__global__ void __launch_bounds__(RS_THREADS, 4) k_rs_onesweep(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                             K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                             int64_t n_host, const uint32_t* n_dev, int shift,
-                                                            const uint32_t* __restrict__ gbase, volatile uint64_t* status,
+                                                            const uint32_t* __restrict__ gbase, uint64_t* status,
                                                             uint32_t gen, uint32_t* ticket) {
     constexpr int ITEMS = RsTraits<K>::ITEMS;
     constexpr int TILE = RS_THREADS * ITEMS;
@@ -86,11 +109,16 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_onesweep(const K* __restrict_
         const int p = wbase + i * 32 + lane;
         k[i] = p < n_valid ? keys_in[base + p] : (K)~(K)0;
     }
-    // stable rank of every key among equal digits of the same warp
+    // stable rank of every key among equal digits of the same warp.  The peer masks are
+    // independent of each other: issue all MATCH instructions first so their latency overlaps,
+    // then run the (inherently serial) per-warp counter chain.
+    uint32_t pm[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) pm[i] = match_digit8((uint32_t)((k[i] >> shift) & 0xff));
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const int d = (int)((k[i] >> shift) & 0xff);
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t peers = pm[i];
         const int leader = __ffs(peers) - 1;
         uint32_t prev = 0;
         if (lane == leader) {
@@ -115,19 +143,38 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_onesweep(const K* __restrict_
         uint32_t total;
         const uint32_t excl_local = block_excl_scan_256(sum, s_scan, &total);
         s_excl[d] = excl_local;
-        // chained scan of this digit's count over tiles
-        volatile uint64_t* st = status + d;
+        // chained scan of this digit's count over tiles: thread d walks back over the tiles,
+        // LB_BATCH predecessors per step (independent loads in flight), so that a wave of W
+        // concurrently running tiles costs W/LB_BATCH dependent L2 round trips.
+        uint64_t* st = status + d;
         uint32_t excl_tiles = 0;
         if (tile == 0) {
-            st[0] = lb_word(gen, sum | LB_INCL);
+            lb_store(st, lb_word(gen, sum | LB_INCL));
         } else {
-            st[(size_t)tile * 256] = lb_word(gen, sum | LB_LOCAL);
-            for (int p = tile - 1; p >= 0; p--) {
-                const uint32_t v = lb_wait(st + (size_t)p * 256, gen);
-                excl_tiles += v & LB_MASK;
-                if ((v >> 30) == 2) break;
+            lb_store(st + (size_t)tile * 256, lb_word(gen, sum | LB_LOCAL));
+            constexpr int LB_BATCH = 8;
+            int p = tile - 1;
+            bool done = false;
+            while (!done) {
+                uint64_t v[LB_BATCH];
+#pragma unroll
+                for (int j = 0; j < LB_BATCH; j++) {
+                    const int q = p - j;
+                    v[j] = q >= 0 ? lb_load(st + (size_t)q * 256) : lb_word(gen, LB_INCL);
+                }
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < LB_BATCH; j++) {
+                    if (!done && used == j && lb_ready(v[j], gen)) {
+                        const uint32_t w = (uint32_t)v[j];
+                        excl_tiles += w & LB_MASK;
+                        used = j + 1;
+                        if ((w >> 30) == 2) done = true;
+                    }
+                }
+                p -= used;  // used == 0: nearest predecessor not published yet -> poll again
             }
-            st[(size_t)tile * 256] = lb_word(gen, (excl_tiles + sum) | LB_INCL);
+            lb_store(st + (size_t)tile * 256, lb_word(gen, (excl_tiles + sum) | LB_INCL));
         }
         s_dst[d] = (int64_t)gbase[d] + (int64_t)excl_tiles - (int64_t)excl_local;
     }
