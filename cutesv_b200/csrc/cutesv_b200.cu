@@ -73,6 +73,19 @@ struct SmallWork {  // DUP / INV / TRA
     DBuf k_rid, k_b, k_prim, perm_a, perm_b, sel, u_chrom, u_a, u_b, u_rid, u_c;
 };
 
+struct ExtractState {
+    DBuf r[7], cigar_off, sa_off, cigar, s[7], piece_off, piece_cnt, pieces, counters;
+    uint32_t* h_counters = nullptr;  // pinned
+    uint32_t n_pieces = 0;
+};
+static void extract_release(ExtractState* x) {
+    for (int k = 0; k < 7; k++) { x->r[k].release(); x->s[k].release(); }
+    x->cigar_off.release(); x->sa_off.release(); x->cigar.release(); x->piece_off.release(); x->piece_cnt.release();
+    x->pieces.release(); x->counters.release();
+    if (x->h_counters) cudaFreeHost(x->h_counters);
+    x->h_counters = nullptr;
+}
+
 struct csv_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;

@@ -124,3 +124,55 @@ class Engine(object):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _lib.check(self.L.csv_result_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+
+def _extract_method(self, packed):
+    """csv_extract on a packing.pack_alignments() packet.  The extracted signatures and reads rows
+    stay device-resident as the inputs of cluster_device(); returns dict(counts, n_rows)."""
+    n = len(packed["chrom"])
+    keep = [np.ascontiguousarray(packed[k], dtype=np.int32) for k in ("chrom", "ref_start", "ref_end", "flag", "mapq", "query_len", "read_id")]
+    co = np.ascontiguousarray(packed["cigar_off"], dtype=np.int64)
+    so = np.ascontiguousarray(packed["sa_off"], dtype=np.int64)
+    rc_ = _abi.csv_read_cols(n, *[_abi.ptr(k) for k in keep], co.ctypes.data_as(C.POINTER(C.c_int64)), so.ctypes.data_as(C.POINTER(C.c_int64)))
+    sa = {k: np.ascontiguousarray(v, dtype=np.int32) for k, v in packed["sa"].items()}
+    sa_ = _abi.csv_sa_cols(len(sa["chrom"]), *[_abi.ptr(sa[k]) for k in ("chrom", "pos0", "strand", "mapq", "first_clip", "last_clip", "ref_span")])
+    cig = np.ascontiguousarray(packed["cigar"], dtype=np.uint32)
+    counts = (C.c_int64 * _abi.CSV_NTYPES)()
+    n_rows = C.c_int64(0)
+    _lib.check(self.L.csv_extract(self.h, C.byref(rc_), cig.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(len(cig)), C.byref(sa_), counts,
+                                  C.byref(n_rows)))
+    self._ex_counts = [int(x) for x in counts]
+    self._ex_rows = int(n_rows.value)
+    return dict(counts={name: int(counts[t]) for t, name in enumerate(_abi.TYPE_NAMES)}, n_rows=int(n_rows.value))
+
+
+def _fetch_extracted_method(self):
+    """D2H of everything csv_extract produced (parity tests / host ALT strings)."""
+    sigs = {}
+    poff = pcnt = None
+    for t, name in enumerate(_abi.TYPE_NAMES):
+        k = self._ex_counts[t]
+        cols = {c: np.zeros(max(k, 1), dtype=np.int32) for c in ("chrom", "a", "b", "read_id", "c")}
+        po = np.zeros(max(k, 1), dtype=np.int32)
+        pc = np.zeros(max(k, 1), dtype=np.int32)
+        _lib.check(self.L.csv_fetch_sigs(self.h, t, C.c_int64(max(k, 1)), _abi.ptr(cols["chrom"]), _abi.ptr(cols["a"]), _abi.ptr(cols["b"]),
+                                         _abi.ptr(cols["read_id"]), _abi.ptr(cols["c"]), _abi.ptr(po), _abi.ptr(pc)))
+        sigs[name] = {c: v[:k] for c, v in cols.items()}
+        if name == "INS":
+            poff, pcnt = po[:k], pc[:k]
+    npz = C.c_int64(0)
+    _lib.check(self.L.csv_fetch_pieces(self.h, C.c_int64(0), None, C.byref(npz)))
+    pieces = np.zeros((max(npz.value, 1), 4), dtype=np.int32)
+    _lib.check(self.L.csv_fetch_pieces(self.h, C.c_int64(len(pieces)), _abi.ptr(pieces), C.byref(npz)))
+    nr = self._ex_rows
+    rows = {k: np.zeros(max(nr, 1), dtype=np.int32) for k in ("chrom", "start", "end", "read_id")}
+    prim = np.zeros(max(nr, 1), dtype=np.uint8)
+    _lib.check(self.L.csv_fetch_read_rows(self.h, C.c_int64(max(nr, 1)), _abi.ptr(rows["chrom"]), _abi.ptr(rows["start"]), _abi.ptr(rows["end"]),
+                                          _abi.ptr(rows["read_id"]), prim.ctypes.data_as(C.POINTER(C.c_uint8))))
+    rows = {k: v[:nr] for k, v in rows.items()}
+    rows["is_primary"] = prim[:nr]
+    return dict(sigs=sigs, piece_off=poff, piece_cnt=pcnt, pieces=pieces[:npz.value], rows=rows)
+
+
+Engine.extract = _extract_method
+Engine.fetch_extracted = _fetch_extracted_method

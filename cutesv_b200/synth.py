@@ -335,3 +335,104 @@ def adversarial(seed, n_contigs=3, max_sigs=400):
                   genotype=int(rng.random() < 0.8))
     return dict(names=names, lens=lens, reads=reads, sigs=sigs, params=params,
                 n_sigs=int(sum(len(v["chrom"]) for v in sigs.values())), config_id=0, scale=0.0)
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic alignment records (extraction stage): duck-typed like pysam.AlignedSegment
+# ----------------------------------------------------------------------------------------------
+class SynthRead(object):
+    __slots__ = ("flag", "mapq", "query_length", "query_name", "query_sequence", "reference_start", "reference_end",
+                 "reference_name", "cigartuples", "cigar", "tags")
+
+    def get_tags(self):
+        return self.tags
+
+
+def _rand_cigar(rng, target_q, noise, sv_rate, clip):
+    """Random CIGAR consuming about target_q query bases.  Returns (tuples, query_len, ref_span)."""
+    ops = []
+    lead = int(rng.integers(0, 400)) if clip and rng.random() < 0.5 else 0
+    if lead:
+        ops.append((5 if rng.random() < 0.2 else 4, lead))
+    q = 0
+    while q < target_q:
+        m = int(rng.integers(5, 400))
+        ops.append((int(rng.choice([0, 7, 8], p=[0.8, 0.15, 0.05])), m))
+        q += m
+        r = rng.random()
+        if r < sv_rate:
+            ln = int(rng.integers(30, 900))
+            ops.append((1 if rng.random() < 0.5 else 2, ln))
+        elif r < sv_rate + noise:
+            ln = int(rng.integers(1, 25))
+            op = int(rng.choice([1, 2, 3, 6]))
+            ops.append((op, ln))
+        if ops[-1][0] == 1:
+            q += ops[-1][1]
+    if ops[-1][0] not in (0, 7, 8):
+        ops.append((0, int(rng.integers(5, 60))))
+    trail = int(rng.integers(0, 400)) if clip and rng.random() < 0.5 else 0
+    if trail:
+        ops.append((5 if rng.random() < 0.2 else 4, trail))
+    qlen = sum(l for o, l in ops if o in (0, 1, 4, 7, 8))
+    span = sum(l for o, l in ops if o in (0, 2, 3, 7, 8))
+    return ops, qlen, span
+
+
+def synth_alignments(seed, n_reads=200, n_contigs=3, with_seq=True):
+    """Alignment records with CIGAR indels, clips and SA tags that hit every branch of
+    analysis_split_read (cuteSV:190-464).  Returns (reads, contig_names, contig_lens)."""
+    rng = np.random.default_rng(seed)
+    names, lens = contigs(1.0, n_contigs)
+    lens = np.minimum(lens, 5000000).astype(np.int64)
+    reads = []
+    for i in range(n_reads):
+        r = SynthRead()
+        r.query_name = read_name(int(rng.integers(0, max(n_reads // 2, 1))) if rng.random() < 0.1 else i)
+        r.flag = int(rng.choice([0, 16, 2048, 2064, 256, 272, 4, 1024], p=[0.4, 0.35, 0.08, 0.07, 0.03, 0.02, 0.03, 0.02]))
+        r.mapq = int(rng.choice([0, 5, 19, 20, 30, 60], p=[0.05, 0.05, 0.05, 0.1, 0.25, 0.5]))
+        ch = int(rng.integers(0, n_contigs))
+        r.reference_name = names[ch]
+        r.reference_start = int(rng.integers(0, 200000))
+        target = int(rng.choice([300, 800, 3000, 12000]))
+        ops, qlen, span = _rand_cigar(rng, target, 0.25, 0.08, True)
+        r.cigartuples = ops
+        r.cigar = ops
+        r.query_length = qlen
+        r.reference_end = r.reference_start + span
+        r.query_sequence = "".join(rng.choice(list("ACGT"), qlen)) if with_seq else None
+        tags = [("NM", 3)]
+        if rng.random() < 0.45:
+            k = int(rng.choice([1, 1, 2, 2, 3, 4, 6, 9]))
+            ents = []
+            # total read length incl. hard clips is what the reference calls total_L = read.query_length
+            L = max(qlen, 50)
+            cuts = np.sort(rng.integers(0, L, 2 * k))
+            for j in range(k):
+                a, b = int(cuts[2 * j]), int(cuts[2 * j + 1])
+                if b <= a:
+                    b = a + 1
+                strand = "+" if rng.random() < 0.6 else "-"
+                sch = names[ch] if rng.random() < 0.7 else names[int(rng.integers(0, n_contigs))]
+                mode = rng.random()
+                if mode < 0.5:
+                    pos = r.reference_end + int(rng.integers(-3000, 3000))
+                elif mode < 0.8:
+                    pos = r.reference_start + int(rng.integers(-3000, 3000))
+                else:
+                    pos = int(rng.integers(1, 300000))
+                pos = max(pos, 1)
+                mid = "%dM" % max(b - a, 1)
+                if rng.random() < 0.3:
+                    mid = "%dM%dD%dM" % (max((b - a) // 2, 1), int(rng.integers(1, 500)), max((b - a) - (b - a) // 2, 1))
+                if rng.random() < 0.2:
+                    mid = "%d=%dI%dX" % (max((b - a) // 2, 1), int(rng.integers(1, 50)), max((b - a) // 3, 1))
+                lead = "%dS" % a if a > 0 and rng.random() < 0.9 else ("%dH" % a if a > 0 else "")
+                trail = "%dS" % (L - b) if L - b > 0 and rng.random() < 0.9 else ("%dH" % (L - b) if L - b > 0 else "")
+                if strand == "-":
+                    lead, trail = trail.replace("S", "S"), lead
+                ents.append("%s,%d,%s,%s%s%s,%d,%d" % (sch, pos, strand, lead, mid, trail, int(rng.choice([0, 10, 20, 60])), 7))
+            tags.append(("SA", ";".join(ents) + ";"))
+        r.tags = tags
+        reads.append(r)
+    return reads, names, lens

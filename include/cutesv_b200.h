@@ -226,17 +226,21 @@ typedef struct csv_sa_cols {
     const int32_t* ref_span;   /* sum of M, D, =, X */
 } csv_sa_cols;
 
-/* Extracted signatures stay device-resident as the inputs of csv_cluster(); counts per type are
- * reported.  cigar[] is BAM-native u32 = len << 4 | op.  INS sequences are not materialised:
- * for every INS signature the (record, query offset, length) triple is returned on request. */
+/* Extracted signatures and reads-table rows REPLACE the device-resident inputs of csv_cluster()
+ * (one packet per call); counts per type are reported.  cigar[] is BAM-native u32 = len << 4 | op.
+ * Replaces Pool#1 (single_pipe/parse_read per window, cuteSV:1058-1076) without the pickle files.
+ * INS sequences are not materialised on the device: every INS signature carries len(seq) in
+ * column c plus a list of "pieces" (Python slices of a record's query sequence, or of its
+ * reverse complement) from which the host rebuilds the string when it needs it. */
 int csv_extract(csv_ctx* ctx, const csv_read_cols* reads, const uint32_t* cigar, int64_t n_cigar,
                 const csv_sa_cols* sa, int64_t counts[CSV_NTYPES], int64_t* n_read_rows);
-/* D2H of the extracted signature columns of one type (for parity tests and .sigs dumps).
- * extra3[3*i..] for INS = (record index, query slice start, query slice stop) with
- * Python-slice semantics on the (possibly reverse-complemented) query; flag bit 30 of the
- * record index marks "slice the reverse complement". */
+/* D2H of the extracted signature columns of one type (parity tests, .sigs dumps, host ALT
+ * strings).  piece_off / piece_cnt (INS only, may be NULL): slice of the piece table. */
 int csv_fetch_sigs(csv_ctx* ctx, int svtype, int64_t cap, int32_t* chrom, int32_t* a, int32_t* b,
-                   int32_t* read_id, int32_t* c, int32_t* extra3);
+                   int32_t* read_id, int32_t* c, int32_t* piece_off, int32_t* piece_cnt);
+/* Piece table: 4 int32 per piece = (record index, slice start, slice stop, reverse-complement flag),
+ * Python slice semantics (negative indices allowed).  *n_pieces reports the table size. */
+int csv_fetch_pieces(csv_ctx* ctx, int64_t cap, int32_t* pieces4, int64_t* n_pieces);
 int csv_fetch_read_rows(csv_ctx* ctx, int64_t cap, int32_t* chrom, int32_t* start, int32_t* end,
                         int32_t* read_id, uint8_t* is_primary);
 

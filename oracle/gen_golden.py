@@ -77,6 +77,16 @@ def main():
         kat.append({"v": v, "cipos": g.cal_CIPOS(np.std(v), len(v)), "std_hex": float(np.std(v)).hex()})
     with open(os.path.join(OUT, "cipos_kat.json"), "w") as f:
         json.dump(kat, f)
+    # extraction: tuples of the reference's parse_read on seeded synthetic alignment packets
+    ex_cases = [("extract_s0", 0, 300, dict()),
+                ("extract_s1", 1, 300, dict(min_mapq=0, max_split_parts=-1, merge_del_threshold=500, merge_ins_threshold=500, min_read_len=100)),
+                ("extract_s2", 2, 400, dict(min_size=50, max_size=-1, min_siglength=30, max_split_parts=3))]
+    for name, seed, n, kw in ex_cases:
+        reads, _, _ = synth.synth_alignments(seed, n)
+        c, r = ref_harness.run_parse_reads(reads, _abi.default_params(**kw))
+        with open(os.path.join(OUT, name + ".json"), "w") as f:
+            json.dump(dict(seed=seed, n_reads=n, params=kw, candidate={k: [list(t) for t in v] for k, v in c.items()},
+                           rows=[list(t) for t in r]), f)
     with open(os.path.join(OUT, "index.json"), "w") as f:
         json.dump(index, f)
     print("cal_gl", len(tab), "cipos", len(kat))

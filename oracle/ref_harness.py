@@ -194,3 +194,20 @@ def run_reference(sigs, reads, chrom_names, read_name, p, types_=("DEL", "INS", 
                                             p.gt_round, sigs_index))
                 res[("TRA", c)] = rows
     return res
+
+
+def run_parse_reads(reads, p):
+    """The reference's extraction loop body (single_pipe, cuteSV:709-733) on in-memory read objects:
+    calls the UNMODIFIED parse_read (cuteSV:606-681).  Returns (candidate dict, reads_info_list)."""
+    main = modules()["main"]
+    candidate = {k: [] for k in ("DEL", "INS", "DUP", "INV", "TRA")}
+    rows = []
+    for read in reads:
+        if read.flag == 256 or read.flag == 272:
+            continue
+        main.parse_read(read, candidate, read.reference_name, p.min_size, p.min_mapq, p.max_split_parts, p.min_read_len,
+                        p.min_siglength, p.merge_del_threshold, p.merge_ins_threshold, p.max_size)
+        if read.mapq >= p.min_mapq:
+            rows.append((read.reference_start, read.reference_end, 1 if read.flag in (0, 16) else 0, read.query_name,
+                         read.reference_name))
+    return candidate, rows

@@ -226,3 +226,79 @@ extern "C" int emul_cluster(const csv_params* P, int32_t n_contigs, const int64_
     }
     return CSV_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// extraction emulator: serial CIGAR walk + the shared per-read logic of extract_core.h
+// ------------------------------------------------------------------------------------------
+#include "../../cutesv_b200/csrc/extract_core.h"
+
+extern "C" int emul_extract(const csv_params* P0, const csv_read_cols* reads, const uint32_t* cigar, const csv_sa_cols* sa,
+                            int32_t* out_cols /* [5 types][5 cols][cap] */, int64_t cap, int32_t* piece_off, int32_t* piece_cnt,
+                            int32_t* pieces4, int64_t cap_pieces, int32_t* rr /* [4][cap_rows] */, uint8_t* rr_prim, int64_t cap_rows,
+                            int64_t counts[8]) {
+    using namespace csv;
+    ExtractParams P;
+    P.min_size = P0->min_size; P.max_size = P0->max_size; P.min_mapq = P0->min_mapq; P.max_split_parts = P0->max_split_parts;
+    P.min_read_len = P0->min_read_len; P.min_siglength = P0->min_siglength; P.merge_del_threshold = P0->merge_del_threshold;
+    P.merge_ins_threshold = P0->merge_ins_threshold;
+    uint32_t ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    ExtractOut O;
+    memset(&O, 0, sizeof(O));
+    for (int t = 0; t < CSV_NTYPES; t++) {
+        for (int k = 0; k < 5; k++) O.col[t][k] = out_cols + ((size_t)t * 5 + k) * cap;
+        O.cap_sig[t] = (uint32_t)cap;
+    }
+    O.n_sig = ctr; O.n_pieces = ctr + 5; O.n_rows = ctr + 6; O.status = ctr + 7;
+    O.ins_piece_off = piece_off; O.ins_piece_cnt = piece_cnt; O.pieces = (InsPiece*)pieces4; O.cap_pieces = (uint32_t)cap_pieces;
+    O.rr_chrom = rr; O.rr_start = rr + cap_rows; O.rr_end = rr + 2 * cap_rows; O.rr_id = rr + 3 * cap_rows; O.rr_prim = rr_prim;
+    O.cap_rows = (uint32_t)cap_rows;
+    SaView S{sa->chrom, sa->pos0, sa->strand, sa->mapq, sa->first_clip, sa->last_clip, sa->ref_span};
+    for (int64_t rec = 0; rec < reads->n; rec++) {
+        const int32_t flag = reads->flag[rec];
+        if (flag == 256 || flag == 272) continue;
+        const int32_t mapq = reads->mapq[rec], qlen = reads->query_len[rec], chrom = reads->chrom[rec], rid = reads->read_id[rec];
+        const bool mq_ok = mapq >= P.min_mapq;
+        if (mq_ok) {
+            uint32_t k = ctr[6]++;
+            if ((int64_t)k < cap_rows) {
+                O.rr_chrom[k] = chrom; O.rr_start[k] = reads->ref_start[rec]; O.rr_end[k] = reads->ref_end[rec]; O.rr_id[k] = rid;
+                O.rr_prim[k] = (flag == 0 || flag == 16) ? 1 : 0;
+            }
+        }
+        if (qlen < P.min_read_len) continue;
+        ReadCtx RC; RC.rec = (int32_t)rec; RC.chrom = chrom; RC.rid = rid; RC.qlen = qlen; RC.base_rc = 0;
+        const int64_t c_lo = reads->cigar_off[rec], c_hi = reads->cigar_off[rec + 1];
+        int32_t clip_l = 0, clip_r = 0;
+        if (mq_ok && c_hi > c_lo) {
+            const uint32_t first = cigar[c_lo], last = cigar[c_hi - 1];
+            const int fop = first & 15, lop = last & 15;
+            const int32_t hard_l = fop == OP_H ? (int32_t)(first >> 4) : 0;
+            if (fop == OP_S || fop == OP_H) clip_l = (int32_t)(first >> 4);
+            if (lop == OP_S || lop == OP_H) clip_r = (int32_t)(last >> 4);
+            MergeState St; St.reset();
+            InsPiece open_pieces[MAX_OPEN_PIECES];
+            int32_t ref = reads->ref_start[rec];
+            int64_t q = -(int64_t)hard_l;
+            for (int64_t i = c_lo; i < c_hi; i++) {
+                const int op = cigar[i] & 15; const int32_t len = (int32_t)(cigar[i] >> 4);
+                if (op != OP_D) q += len;
+                if (len >= P.min_siglength && (op == OP_I || op == OP_D)) {
+                    if (op == OP_D) { push_del(O, RC, P, St, ref, len); ref += len; }
+                    else push_ins(O, RC, P, St, open_pieces, ref, len, q - len, q);
+                } else if (op_ref_change(op)) ref += len;
+            }
+            flush_ins(O, RC, St, open_pieces); flush_del(O, RC, St);
+        }
+        const int sig = detect_flag(flag);
+        const int64_t s_lo = reads->sa_off[rec], s_hi = reads->sa_off[rec + 1];
+        if ((sig == 1 || sig == 2) && s_hi > s_lo) {
+            SplitCtx C; C.O = &O; C.R = RC; C.P = P; C.R.base_rc = sig == 2 ? 1 : 0;
+            Seg prim;
+            if (sig == 1) { prim.rs = clip_l; prim.re = qlen - clip_r; } else { prim.rs = clip_r; prim.re = qlen - clip_l; }
+            prim.fs = reads->ref_start[rec]; prim.fe = reads->ref_end[rec]; prim.chr = chrom; prim.strand = sig == 1 ? 0 : 1;
+            organize_split_signal(C, mq_ok, prim, S, s_lo, s_hi);
+        }
+    }
+    for (int k = 0; k < 8; k++) counts[k] = ctr[k];
+    return CSV_OK;
+}
