@@ -388,8 +388,10 @@ def synth_alignments(seed, n_reads=200, n_contigs=3, with_seq=True):
     reads = []
     for i in range(n_reads):
         r = SynthRead()
-        r.query_name = read_name(int(rng.integers(0, max(n_reads // 2, 1))) if rng.random() < 0.1 else i)
         r.flag = int(rng.choice([0, 16, 2048, 2064, 256, 272, 4, 1024], p=[0.4, 0.35, 0.08, 0.07, 0.03, 0.02, 0.03, 0.02]))
+        # a read name has ONE primary record; supplementary records re-use the names of other reads
+        reuse = r.flag not in (0, 16) and rng.random() < 0.6
+        r.query_name = read_name(int(rng.integers(0, max(n_reads // 2, 1))) if reuse else i)
         r.mapq = int(rng.choice([0, 5, 19, 20, 30, 60], p=[0.05, 0.05, 0.05, 0.1, 0.25, 0.5]))
         ch = int(rng.integers(0, n_contigs))
         r.reference_name = names[ch]
