@@ -95,6 +95,13 @@ CSV_HD int pow2ceil(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 template <class Team>
 CSV_HD int64_t team_sum(Team tm, int64_t v, int64_t* red) {
+#if defined(__CUDA_ARCH__)
+    if (Team::SIZE == 32) {  // warp team: shuffles, no shared memory round trips
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+#endif
     const int t = tm.tid();
     red[t] = v;
     tm.sync();
@@ -108,6 +115,13 @@ CSV_HD int64_t team_sum(Team tm, int64_t v, int64_t* red) {
 }
 template <class Team>
 CSV_HD int64_t team_min(Team tm, int64_t v, int64_t* red) {
+#if defined(__CUDA_ARCH__)
+    if (Team::SIZE == 32) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const int64_t y = __shfl_xor_sync(0xffffffffu, v, o); if (y < v) v = y; }
+        return v;
+    }
+#endif
     const int t = tm.tid();
     red[t] = v;
     tm.sync();
@@ -136,6 +150,18 @@ CSV_HD uint32_t team_excl_scan(Team tm, uint32_t* arr, int n, int64_t* red) {
     int hi = lo + chunk; if (hi > n) hi = n;
     uint32_t s = 0;
     for (int i = lo; i < hi; i++) s += arr[i];
+#if defined(__CUDA_ARCH__)
+    if (Team::SIZE == 32) {
+        uint32_t incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (t >= d) incl += y; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t run = incl - s;
+        for (int i = lo; i < hi; i++) { uint32_t x = arr[i]; arr[i] = run; run += x; }
+        tm.sync();
+        return total;
+    }
+#endif
     red[t] = s;
     tm.sync();
     if (t == 0) {
@@ -165,6 +191,24 @@ CSV_HD void team_sort_k128(Team tm, K128* a, int M) {
                     bool up = (i & k) == 0;
                     K128 x = a[i], y = a[l];
                     if (k128_gt(x, y) == up) { a[i] = y; a[l] = x; }
+                }
+            }
+            tm.sync();
+        }
+}
+template <class Team>
+CSV_HD void team_sort_k128_kv(Team tm, K128* a, uint32_t* v, int M) {
+    for (int k = 2; k <= M; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tm.tid(); i < M; i += Team::SIZE) {
+                int l = i ^ j;
+                if (l > i) {
+                    bool up = (i & k) == 0;
+                    K128 x = a[i], y = a[l];
+                    if (k128_gt(x, y) == up) {
+                        a[i] = y; a[l] = x;
+                        uint32_t vx = v[i]; v[i] = v[l]; v[l] = vx;
+                    }
                 }
             }
             tm.sync();
@@ -353,7 +397,10 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
     int32_t* ar_a = A.A1;
     int32_t* ar_aux = A.A1 + M;
     int32_t* ar_idx = A.A1 + 2 * M;
-    // 1. load members, build the full sort key (pos, len, name, arrival) -- cuteSV:764,774
+    // 1. load members.  ONE sort by (read, pos, len, arrival) serves three purposes at once:
+    //    exact duplicates become adjacent (remove_duplicates_sorted, cuteSV:958-969), every read's
+    //    signatures become one run whose first element is the read's first occurrence in the
+    //    reference's (pos, len, name) order (cuteSV:764,774), and the run is in that order.
     for (int j = t; j < M; j += Team::SIZE) {
         K128 k;
         if (j < m) {
@@ -363,8 +410,8 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
             ar_a[j] = a;
             ar_aux[j] = in.c ? in.c[i] : 0;
             ar_idx[j] = (int32_t)i;
-            k.hi = pack64((uint32_t)pos, ord32(in.b[i]));
-            k.lo = pack64(ord32(in.rid[i]), (uint32_t)j);
+            k.hi = pack64(ord32(in.rid[i]), (uint32_t)pos);
+            k.lo = pack64(ord32(in.b[i]), (uint32_t)j);
         } else {
             k.hi = ~0ull; k.lo = ~0ull;
         }
@@ -372,7 +419,7 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
     }
     tm.sync();
     team_sort_k128(tm, A.A0, M);
-    // 2. remove_duplicates_sorted (cuteSV:958-969): adjacent identical tuples
+    // 2. remove_duplicates_sorted: adjacent identical tuples
     auto keep_fn = [&](int q) -> bool {
         if (q == 0) return true;
         K128 x = A.A0[q], y = A.A0[q - 1];
@@ -390,7 +437,7 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
             K128 x = A.A0[q];
             int j = (int)lo32(x.lo);
             uint32_t d = A.F[q];
-            D_pos[d] = (int32_t)hi32(x.hi); D_len[d] = unord32(lo32(x.hi)); D_rid[d] = unord32(hi32(x.lo));
+            D_pos[d] = (int32_t)lo32(x.hi); D_len[d] = unord32(hi32(x.lo)); D_rid[d] = unord32(hi32(x.hi));
             D_aux[d] = ar_aux[j]; D_idx[d] = ar_idx[j];
         }
     }
@@ -399,40 +446,39 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
         if (t == 0) E.cnt[kslot] = 0;
         return;
     }
-    // 3. per-read dedup (resolveINDEL.py:125-131): group by read, first-occurrence order
-    uint64_t* K2 = (uint64_t*)A.A0;
-    const int M2 = pow2ceil(m2);
-    for (int q = t; q < M2; q += Team::SIZE) K2[q] = q < m2 ? pack64(ord32(D_rid[q]), (uint32_t)q) : ~0ull;
+    // 3. per-read dedup (resolveINDEL.py:125-131): one entry per read = its longest signature
+    //    (strictly larger replaces), kept at the dict position of the read's first occurrence
+    for (int q = t; q < m2; q += Team::SIZE) A.F[q] = (q == 0 || D_rid[q] != D_rid[q - 1]) ? 1u : 0u;
     tm.sync();
-    team_sort_u64(tm, K2, M2);
-    for (int q = t; q < m2; q += Team::SIZE) A.F[q] = (q == 0 || hi32(K2[q]) != hi32(K2[q - 1])) ? 1u : 0u;
-    tm.sync();
-    // heads are recomputed after the scan overwrote the flags
     const int u = (int)team_excl_scan(tm, A.F, m2, red);
     if (u < P.min_support) {  // len(read_tag) < read_count (:133)
         if (t == 0) E.cnt[kslot] = 0;
         return;
     }
-    uint64_t* K3 = (uint64_t*)A.A1;          // 8 B * M
-    uint32_t* V3 = (uint32_t*)(A.A1 + 2 * M);  // 4 B * M
+    K128* K3 = A.A0;               // sort-1 keys are dead: everything lives in the D arrays now
+    uint32_t* V3 = (uint32_t*)A.A1;  // arrival arrays are dead too
     const int M3 = pow2ceil(u);
     for (int q = t; q < m2; q += Team::SIZE) {
-        bool head = q == 0 || hi32(K2[q]) != hi32(K2[q - 1]);
+        const bool head = q == 0 || D_rid[q] != D_rid[q - 1];
         if (head) {
-            uint32_t first = lo32(K2[q]);
-            uint32_t best = first;
-            for (int r = q + 1; r < m2 && hi32(K2[r]) == hi32(K2[q]); r++) {
-                uint32_t e = lo32(K2[r]);
-                if (D_len[e] > D_len[best]) best = e;  // strictly larger replaces (:130)
-            }
-            uint32_t g = A.F[q];
-            K3[g] = pack64(ord32(D_len[best]), first);  // sorted(..., key=len), stable on dict order (:136)
-            V3[g] = best;
+            int best = q;
+            for (int r = q + 1; r < m2 && D_rid[r] == D_rid[q]; r++)
+                if (D_len[r] > D_len[best]) best = r;  // strictly larger replaces (:130)
+            const uint32_t g = A.F[q];
+            // sorted(read_tag.values(), key=len) is stable on the dict order = order of first occurrence in the
+            // (pos, len, name) sorted cluster; names differ between reads, so (pos, len, name) of the first
+            // occurrence is a total tie-break
+            K128 k;
+            k.hi = pack64(ord32(D_len[best]), (uint32_t)D_pos[q]);
+            k.lo = pack64(ord32(D_len[q]), ord32(D_rid[q]));
+            K3[g] = k;
+            V3[g] = (uint32_t)best;
         }
     }
-    for (int q = u + t; q < M3; q += Team::SIZE) { K3[q] = ~0ull; V3[q] = 0; }
     tm.sync();
-    team_sort_kv(tm, K3, V3, M3);
+    for (int q = u + t; q < M3; q += Team::SIZE) { K128 k; k.hi = ~0ull; k.lo = ~0ull; K3[q] = k; V3[q] = 0; }
+    tm.sync();
+    team_sort_k128_kv(tm, K3, V3, M3);
     // 4. allele split on the length-sorted unique reads (:137-162)
     int64_t part = 0;
     for (int i = t; i < u; i += Team::SIZE) part += D_len[V3[i]];
@@ -512,11 +558,15 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
         const double breakpointStart = (double)kept_pos_sum / (double)remain;
         const double signalLen = (double)kept_len_sum / (double)remain;
         // CIPOS / CILEN: np.std over the whole allele (:191-194); two lanes work concurrently
-        if (t == 0) {
+        if (Team::SIZE > 1) {
+            if (t < 2) {  // lanes 0 / 1 run the SAME instruction stream on pos / len
+                const int32_t* src = t == 0 ? D_pos : D_len;
+                auto gv = [&](int64_t i) { return (int64_t)src[V3[st + i]]; };
+                red[t] = cal_cipos(np_std(gv, n, t == 0 ? sp : sl), n, E.pow_half);
+            }
+        } else {
             auto gp = [&](int64_t i) { return (int64_t)D_pos[V3[st + i]]; };
             red[0] = cal_cipos(np_std(gp, n, sp), n, E.pow_half);
-        }
-        if (t == (Team::SIZE > 1 ? 1 : 0)) {
             auto gl = [&](int64_t i) { return (int64_t)D_len[V3[st + i]]; };
             red[1] = cal_cipos(np_std(gl, n, sl), n, E.pow_half);
         }
