@@ -397,6 +397,7 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
     int32_t* ar_a = A.A1;
     int32_t* ar_aux = A.A1 + M;
     int32_t* ar_idx = A.A1 + 2 * M;
+    uint32_t* SJ = (uint32_t*)A.KA;  // 4 B * M inside the (still unused) allele-key region
     // 1. load members.  ONE sort by (read, pos, len, arrival) serves three purposes at once:
     //    exact duplicates become adjacent (remove_duplicates_sorted, cuteSV:958-969), every read's
     //    signatures become one run whose first element is the read's first occurrence in the
@@ -411,20 +412,21 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
             ar_aux[j] = in.c ? in.c[i] : 0;
             ar_idx[j] = (int32_t)i;
             k.hi = pack64(ord32(in.rid[i]), (uint32_t)pos);
-            k.lo = pack64(ord32(in.b[i]), (uint32_t)j);
+            k.lo = pack64(ord32(in.b[i]), i);   // ties: original input index (independent of arrival order)
         } else {
             k.hi = ~0ull; k.lo = ~0ull;
         }
         A.A0[j] = k;
+        SJ[j] = (uint32_t)j;                     // payload: arrival slot (addresses ar_a / ar_aux / ar_idx)
     }
     tm.sync();
-    team_sort_k128(tm, A.A0, M);
+    team_sort_k128_kv(tm, A.A0, SJ, M);
     // 2. remove_duplicates_sorted: adjacent identical tuples
     auto keep_fn = [&](int q) -> bool {
         if (q == 0) return true;
         K128 x = A.A0[q], y = A.A0[q - 1];
         if (x.hi != y.hi || hi32(x.lo) != hi32(y.lo)) return true;
-        int jx = (int)lo32(x.lo), jy = (int)lo32(y.lo);
+        int jx = (int)SJ[q], jy = (int)SJ[q - 1];
         return !(ar_a[jx] == ar_a[jy] && ar_aux[jx] == ar_aux[jy]);
     };
     for (int q = t; q < m; q += Team::SIZE) A.F[q] = keep_fn(q) ? 1u : 0u;
@@ -435,7 +437,7 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
     for (int q = t; q < m; q += Team::SIZE) {
         if (keep_fn(q)) {
             K128 x = A.A0[q];
-            int j = (int)lo32(x.lo);
+            int j = (int)SJ[q];
             uint32_t d = A.F[q];
             D_pos[d] = (int32_t)lo32(x.hi); D_len[d] = unord32(hi32(x.lo)); D_rid[d] = unord32(hi32(x.hi));
             D_aux[d] = ar_aux[j]; D_idx[d] = ar_idx[j];

@@ -104,7 +104,8 @@ struct csv_ctx {
     int64_t n_reads = 0;
     DBuf r_chrom, r_start, r_end, r_id, r_prim;
     // sort workspace
-    DBuf keys_a, keys_b, vals_a, vals_b, hist, lb_status, tickets;
+    DBuf keys_a, keys_b, vals_a, vals_b, hist, lb_status, tickets, bkt, bkt_flags;
+    bool prefilter_enabled = true;
     uint32_t gen = 1;
     int ticket_next = 0;
     SmallWork small;
@@ -264,7 +265,7 @@ extern "C" int csv_destroy(csv_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DBuf* all[] = {&c->d_off, &c->d_len, &c->r_chrom, &c->r_start, &c->r_end, &c->r_id, &c->r_prim, &c->keys_a, &c->keys_b,
-                   &c->vals_a, &c->vals_b, &c->hist, &c->lb_status, &c->tickets, &c->big_list, &c->giant_list, &c->giant_arena,
+                   &c->vals_a, &c->vals_b, &c->hist, &c->lb_status, &c->tickets, &c->bkt, &c->bkt_flags, &c->big_list, &c->giant_list, &c->giant_arena,
                    &c->cnt, &c->cand_tmp, &c->cand, &c->geno, &c->names, &c->counters, &c->bin_start, &c->bin_fill, &c->bin_bits, &c->pairs, &c->win_list,
                    &c->dr, &c->has_rows, &c->gl_table, &c->pow_half, &c->small.k_rid, &c->small.k_b, &c->small.k_prim,
                    &c->small.perm_a, &c->small.perm_b, &c->small.sel, &c->small.u_chrom, &c->small.u_a, &c->small.u_b,
@@ -515,13 +516,34 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
     memset(&J, 0, sizeof(J));
     J.svtype = t; J.n_host = n; J.n_dev = nullptr;
     J.cp = cluster_params(c->P, t);
+    // density pre-filter: worthwhile when the expected neighbourhood count is below min_support
+    const uint32_t radius = (uint32_t)std::min<int64_t>((int64_t)(J.cp.min_support - 1) * J.cp.bias, 1 << 24);
+    const double lambda = (double)n * (2.0 * radius + 2.0 * (1 << BKT_SHIFT)) / (double)std::max<uint64_t>(total, 1);
+    const int rb = (int)((radius + (1u << BKT_SHIFT) - 1) >> BKT_SHIFT);  // neighbourhood radius in buckets (conservative)
+    const bool prefilter = !k64 && c->prefilter_enabled && J.cp.min_support >= 3 && lambda < 0.8 * J.cp.min_support &&
+                           n >= (1 << 16) && rb <= BKT_PAD;
+    const size_t n_bkt = (size_t)(total >> BKT_SHIFT) + 2 * BKT_PAD + 2;
     stage_begin(c, CSV_ST_KEYS);
-    if (!k64)
-        LAUNCH(c, (k_indel_keys<uint32_t>), grid_for(c, n, 256), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(),
-               s.rid.as<int32_t>(), n, t == CSV_INS ? 1 : 0, ct, c->keys_a.as<uint32_t>(), &ctr->status);
+    if (prefilter) {
+        CU(c->bkt.ensure(n_bkt * 4));
+        CU(cudaMemsetAsync(c->bkt.p, 0, n_bkt * 4, c->stream));
+        LAUNCH(c, (k_indel_keys<uint32_t, true>), grid_for(c, n, 256), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(),
+               s.rid.as<int32_t>(), n, t == CSV_INS ? 1 : 0, ct, c->keys_b.as<uint32_t>(), &ctr->status, c->bkt.as<uint32_t>());
+        uint32_t* n_pass = &ctr->pad[3];  // re-used per INDEL type: consumed by kernels enqueued before the next type resets it
+        CU(cudaMemsetAsync(n_pass, 0, 4, c->stream));
+        const uint32_t n_buckets = (uint32_t)(total >> BKT_SHIFT) + 1;
+        CU(c->bkt_flags.ensure(((size_t)n_buckets / 32 + 2) * 4));
+        LAUNCH(c, k_bucket_flags, grid_for(c, n_buckets, 256, 8), 256, 0, c->bkt.as<uint32_t>(), n_buckets, rb, (uint32_t)J.cp.min_support,
+               c->bkt_flags.as<uint32_t>());
+        LAUNCH(c, k_prefilter, grid_for(c, n, 2048, 8), 256, 0, c->keys_b.as<uint32_t>(), n, c->bkt_flags.as<uint32_t>(),
+               c->keys_a.as<uint32_t>(), c->vals_a.as<uint32_t>(), n_pass);
+        J.n_dev = n_pass;
+    } else if (!k64)
+        LAUNCH(c, (k_indel_keys<uint32_t, false>), grid_for(c, n, 256), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(),
+               s.rid.as<int32_t>(), n, t == CSV_INS ? 1 : 0, ct, c->keys_a.as<uint32_t>(), &ctr->status, (uint32_t*)nullptr);
     else
-        LAUNCH(c, (k_indel_keys<uint64_t>), grid_for(c, n, 256), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(),
-               s.rid.as<int32_t>(), n, t == CSV_INS ? 1 : 0, ct, c->keys_a.as<uint64_t>(), &ctr->status);
+        LAUNCH(c, (k_indel_keys<uint64_t, false>), grid_for(c, n, 256), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(),
+               s.rid.as<int32_t>(), n, t == CSV_INS ? 1 : 0, ct, c->keys_a.as<uint64_t>(), &ctr->status, (uint32_t*)nullptr);
     stage_end(c, CSV_ST_KEYS);
     stage_begin(c, CSV_ST_SORT);
     uint32_t* sidx = nullptr;
@@ -529,7 +551,7 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
     if (!k64) {
         uint32_t* ko = nullptr;
         rc = radix_sort<uint32_t>(c, c->keys_a.as<uint32_t>(), c->vals_a.as<uint32_t>(), c->keys_b.as<uint32_t>(),
-                                  c->vals_b.as<uint32_t>(), true, n, nullptr, bits, &ko, &sidx);
+                                  c->vals_b.as<uint32_t>(), !prefilter, n, J.n_dev, bits, &ko, &sidx);
         J.keys32 = ko;
     } else {
         uint64_t* ko = nullptr;
@@ -718,7 +740,7 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
                 CU(c->pairs.ensure((size_t)PB.cap * sizeof(uint2)));
                 PB.pairs = c->pairs.as<uint2>();
                 PB.count = &ctr->n_windows;
-                LAUNCH(c, k_reads_pass, grid_for(c, c->n_reads, 256, 8), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                LAUNCH(c, k_reads_pass, grid_for(c, c->n_reads, 1024, 8), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
                        c->r_end.as<int32_t>(), c->r_id.as<int32_t>(), c->r_prim.as<uint8_t>(), c->n_reads, &ctr->status);
                 LAUNCH(c, k_pairs_test, c->n_sm * 8, 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
                        c->r_end.as<int32_t>(), c->r_id.as<int32_t>());

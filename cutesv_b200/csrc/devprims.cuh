@@ -94,6 +94,19 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_
     return r;
 }
 
+// Unordered append: every thread of a 256-thread CTA asks for `cnt` slots of a global buffer; ONE
+// atomicAdd per CTA reserves the whole range (a same-address returning atomic per warp serialises
+// at the L2 slice: 262 k of them cost ~0.2 ms on B200).  Returns the thread's first slot.
+__device__ __forceinline__ uint32_t block_reserve_256(uint32_t cnt, uint32_t* counter, uint32_t* s_warp /*10 words*/) {
+    uint32_t total;
+    const uint32_t local = block_excl_scan_256(cnt, s_warp, &total);
+    if (threadIdx.x == 0) s_warp[9] = total ? atomicAdd(counter, total) : 0u;
+    __syncthreads();
+    const uint32_t base = s_warp[9];
+    __syncthreads();
+    return base + local;
+}
+
 static constexpr int SEL_THREADS = 256;
 static constexpr int SEL_ITEMS = 8;
 static constexpr int SEL_TILE = SEL_THREADS * SEL_ITEMS;
