@@ -44,6 +44,7 @@ _SIGNATURES = {
     "csv_set_profiling": (C.c_int, [_VP, C.c_int]),
     "csv_stage_ms": (C.c_int, [_VP, C.POINTER(C.c_float)]),
     "csv_launch_count": (C.c_int64, [_VP]),
+    "csv_debug_counters": (C.c_int, [_VP, C.POINTER(C.c_uint32)]),
     "csv_sort_probe": (C.c_int, [_VP, C.POINTER(C.c_float), _I64P, C.POINTER(C.c_int32)]),
 }
 EXPORTS = tuple(sorted(_SIGNATURES))

@@ -70,8 +70,11 @@ struct Counters {
     uint32_t n_kept[CSV_NTYPES];   // kept chain clusters per type
     uint32_t n_big[CSV_NTYPES];    // deferred to the CTA-sized team
     uint32_t n_giant[CSV_NTYPES];  // deferred to the global-scratch team
-    uint32_t n_windows;     // genotype windows
-    uint32_t pad[4];
+    uint32_t n_windows;     // (read, window) pairs of the genotype pass
+    uint32_t n_dom[CSV_NTYPES];    // size of the sorted domain per type when only the device knows it
+                                   // (INDEL: survivors of the density filter; others: after duplicate removal)
+    uint32_t n_members[CSV_NTYPES]; // signatures inside kept chain clusters (roofline accounting)
+    uint32_t pad[2];
 };
 
 struct Limits {

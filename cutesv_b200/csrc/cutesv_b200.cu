@@ -124,7 +124,7 @@ struct csv_ctx {
     int64_t launches = 0;
     // profiling: CUDA-event intervals on the ctx stream; a stage may be entered once per SV type
     bool profiling = false;
-    struct Interval { int st; cudaEvent_t a, b; int64_t bytes; };
+    struct Interval { int st; cudaEvent_t a, b; int64_t bytes; int dom_type; int64_t per_elem; };
     std::vector<Interval> ivs;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_next = 0;
@@ -173,11 +173,11 @@ static cudaEvent_t pool_event(csv_ctx* c) {
 static void stage_reset_if_consumed(csv_ctx* c) {
     if (c->ivs_consumed) { c->ivs.clear(); c->ev_next = 0; c->ivs_consumed = false; }
 }
-static void stage_begin(csv_ctx* c, int st, int64_t bytes = 0) {
+static void stage_begin(csv_ctx* c, int st, int64_t bytes = 0, int dom_type = -1, int64_t per_elem = 0) {
     if (!c->profiling) return;
     stage_reset_if_consumed(c);
     csv_ctx::Interval iv;
-    iv.st = st; iv.a = pool_event(c); iv.b = pool_event(c); iv.bytes = bytes;
+    iv.st = st; iv.a = pool_event(c); iv.b = pool_event(c); iv.bytes = bytes; iv.dom_type = dom_type; iv.per_elem = per_elem;
     cudaEventRecord(iv.a, c->stream);
     c->ivs.push_back(iv);
 }
@@ -192,7 +192,11 @@ static void stage_collect(csv_ctx* c) {  // after a stream synchronize
     for (const csv_ctx::Interval& iv : c->ivs) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, iv.a, iv.b) != cudaSuccess) { cudaGetLastError(); continue; }
-        if (iv.st == ST_SORT_PASS) { c->sort_ms += t; c->sort_bytes += iv.bytes; c->sort_launches++; }
+        if (iv.st == ST_SORT_PASS) {
+            int64_t bytes = iv.bytes;
+            if (iv.dom_type >= 0 && c->h_counters) bytes = (int64_t)c->h_counters->n_dom[iv.dom_type] * iv.per_elem;  // device-sized domain
+            c->sort_ms += t; c->sort_bytes += bytes; c->sort_launches++;
+        }
         else c->stage_ms[iv.st] += t;
     }
     c->ivs_consumed = true;
@@ -410,7 +414,7 @@ static int make_sync(csv_ctx* c, size_t status_words, TileSync* ts) {
 // ------------------------------------------------------------------------------------------
 template <typename K>
 static int radix_sort(csv_ctx* c, K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* vals_b, bool iota, int64_t n,
-                      const uint32_t* n_dev, int bits, K** keys_out, uint32_t** vals_out) {
+                      const uint32_t* n_dev, int bits, K** keys_out, uint32_t** vals_out, int dom_type = -1) {
     const int passes = std::max(1, (bits + 7) / 8);
     if (passes > RS_MAX_PASSES) return set_err(CSV_E_INVALID, "radix sort: %d bits", bits);
     constexpr int TILE = RS_THREADS * RsTraits<K>::ITEMS;
@@ -425,7 +429,8 @@ static int radix_sort(csv_ctx* c, K* keys_a, uint32_t* vals_a, K* keys_b, uint32
         TileSync ts;
         int rc = make_sync(c, (size_t)n_tiles * 256, &ts);
         if (rc) return rc;
-        stage_begin(c, ST_SORT_PASS, n * (int64_t)(sizeof(K) + ((p == 0 && iota) ? 0 : 4) + sizeof(K) + 4));
+        const int64_t per_elem = (int64_t)(sizeof(K) + ((p == 0 && iota) ? 0 : 4) + sizeof(K) + 4);
+        stage_begin(c, ST_SORT_PASS, n * per_elem, n_dev ? dom_type : -1, per_elem);
         if (p == 0 && iota)
             LAUNCH(c, (k_rs_onesweep<K, true>), (int)n_tiles, RS_THREADS, 0, ki, (const uint32_t*)nullptr, ko, vo, n, n_dev, 8 * p,
                    c->hist.as<uint32_t>() + p * 256, ts.status, ts.gen, ts.ticket);
@@ -529,8 +534,7 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
         CU(cudaMemsetAsync(c->bkt.p, 0, n_bkt * 4, c->stream));
         LAUNCH(c, (k_indel_keys<uint32_t, true>), grid_for(c, n, 256), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(),
                s.rid.as<int32_t>(), n, t == CSV_INS ? 1 : 0, ct, c->keys_b.as<uint32_t>(), &ctr->status, c->bkt.as<uint32_t>());
-        uint32_t* n_pass = &ctr->pad[3];  // re-used per INDEL type: consumed by kernels enqueued before the next type resets it
-        CU(cudaMemsetAsync(n_pass, 0, 4, c->stream));
+        uint32_t* n_pass = &ctr->n_dom[t];
         const uint32_t n_buckets = (uint32_t)(total >> BKT_SHIFT) + 1;
         CU(c->bkt_flags.ensure(((size_t)n_buckets / 32 + 2) * 4));
         LAUNCH(c, k_bucket_flags, grid_for(c, n_buckets, 256, 8), 256, 0, c->bkt.as<uint32_t>(), n_buckets, rb, (uint32_t)J.cp.min_support,
@@ -551,7 +555,7 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
     if (!k64) {
         uint32_t* ko = nullptr;
         rc = radix_sort<uint32_t>(c, c->keys_a.as<uint32_t>(), c->vals_a.as<uint32_t>(), c->keys_b.as<uint32_t>(),
-                                  c->vals_b.as<uint32_t>(), !prefilter, n, J.n_dev, bits, &ko, &sidx);
+                                  c->vals_b.as<uint32_t>(), !prefilter, n, J.n_dev, bits, &ko, &sidx, t);
         J.keys32 = ko;
     } else {
         uint64_t* ko = nullptr;
@@ -606,7 +610,7 @@ static int run_other(csv_ctx* c, int t, uint32_t kslot_base) {
     stage_end(c, CSV_ST_SORT);
     // exact-duplicate removal + materialise the sorted columns
     stage_begin(c, CSV_ST_SEGMENT);
-    uint32_t* n_u = &ctr->pad[t - CSV_INV];  // device-side size of the de-duplicated domain (one slot per small type)
+    uint32_t* n_u = &ctr->n_dom[t];  // device-side size of the de-duplicated domain
     TileSync ts;
     rc = make_sync(c, (size_t)(n / SEL_TILE + 2), &ts);
     if (rc) return rc;
@@ -862,6 +866,12 @@ extern "C" int csv_stage_ms(csv_ctx* c, float ms[CSV_ST_COUNT]) {
     return CSV_OK;
 }
 extern "C" int64_t csv_launch_count(csv_ctx* c) { return c ? c->launches : 0; }
+extern "C" int csv_debug_counters(csv_ctx* c, uint32_t out[32]) {
+    if (!c || !out || !c->h_counters) return set_err(CSV_E_INVALID, "null argument");
+    static_assert(sizeof(Counters) == 32 * 4, "Counters layout");
+    memcpy(out, c->h_counters, 32 * 4);
+    return CSV_OK;
+}
 
 extern "C" int csv_sort_probe(csv_ctx* c, float* ms_total, int64_t* bytes_total, int32_t* launches) {
     if (!c) return set_err(CSV_E_INVALID, "null ctx");

@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(CL_THREADS) k_cluster_warp(TypeJob J, Emit E, 
             }
             continue;
         }
+        if (lane == 0) atomicAdd(&ctr->n_members[J.svtype], (uint32_t)m);
         run_cluster(tm, J, s, m, pow2ceil(m), arena, red, J.kslot_base + k, E);
         __syncwarp();
     }
@@ -389,6 +390,7 @@ __global__ void __launch_bounds__(CL_THREADS) k_cluster_block(TypeJob J, Emit E,
             continue;
         }
         const int M = pow2ceil((int)m);
+        if (threadIdx.x == 0) atomicAdd(&ctr->n_members[J.svtype], (uint32_t)m);
         // global scratch: clusters are disjoint ranges of the sorted order and M <= 2m
         char* arena = GIANT ? (J.giant_arena + (size_t)(2 * s) * ARENA_PER_MAX) : smem;
         run_cluster(tm, J, s, (int)m, M, arena, red, J.kslot_base + k, E);

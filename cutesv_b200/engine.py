@@ -117,6 +117,14 @@ class Engine(object):
         _lib.check(self.L.csv_sort_probe(self.h, C.byref(ms), C.byref(b), C.byref(n)))
         return dict(ms=float(ms.value), bytes=int(b.value), launches=int(n.value))
 
+    def counters(self):
+        out = (C.c_uint32 * 32)()
+        _lib.check(self.L.csv_debug_counters(self.h, out))
+        v = list(out)
+        t = _abi.TYPE_NAMES
+        return dict(status=v[0], n_cand=v[1], n_names=v[2], max_support=v[3], kept=dict(zip(t, v[4:9])), big=dict(zip(t, v[9:14])),
+                    giant=dict(zip(t, v[14:19])), pairs=v[19], domain=dict(zip(t, v[20:25])), members=dict(zip(t, v[25:30])))
+
     def launch_count(self):
         return int(self.L.csv_launch_count(self.h))
 

@@ -249,6 +249,11 @@ int csv_set_profiling(csv_ctx* ctx, int on);
 int csv_stage_ms(csv_ctx* ctx, float ms[CSV_ST_COUNT]);
 /* Number of kernels the library launched since the ctx was created. */
 int64_t csv_launch_count(csv_ctx* ctx);
+/* Device counters of the last finished csv_cluster call, 32 words: [0] status, [1] candidates,
+ * [2] names, [3] max support, [4..8] kept clusters per type, [9..13] CTA-class clusters,
+ * [14..18] global-scratch-class clusters, [19] (read, window) pairs, [20..24] sorted-domain size per
+ * type, [25..29] signatures inside kept clusters per type. */
+int csv_debug_counters(csv_ctx* ctx, uint32_t out[32]);
 /* Duration (ms) and element count of the last radix scatter pass launches (roofline probe). */
 int csv_sort_probe(csv_ctx* ctx, float* ms_total, int64_t* bytes_total, int32_t* launches);
 
