@@ -87,6 +87,18 @@ def main():
         with open(os.path.join(OUT, name + ".json"), "w") as f:
             json.dump(dict(seed=seed, n_reads=n, params=kw, candidate={k: [list(t) for t in v] for k, v in c.items()},
                            rows=[list(t) for t in r]), f)
+    # the parity sink: VCF records the reference's generate_output + SVID loop produce from its own rows
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_util
+    import vcf_util
+    for name in ("adv034", "adv144", "cfg3_s0p004", "cfg2_s0p002"):
+        case = golden_util.load_case(name)
+        byc = vcf_util.rows_by_chrom(case["rows"])
+        refseq = vcf_util.synthetic_reference(case["names"], [min(int(x), 6000000) for x in case["lens"]])
+        lines = ref_harness.reference_vcf_lines(byc, refseq, bool(case["params"].genotype))
+        with open(os.path.join(OUT, "vcf_%s.json" % name), "w") as f:
+            json.dump(lines, f)
+        print("vcf", name, len(lines))
     with open(os.path.join(OUT, "index.json"), "w") as f:
         json.dump(index, f)
     print("cal_gl", len(tab), "cipos", len(kat))

@@ -211,3 +211,46 @@ def run_parse_reads(reads, p):
             rows.append((read.reference_start, read.reference_end, 1 if read.flag in (0, 16) else 0, read.query_name,
                          read.reference_name))
     return candidate, rows
+
+
+class _Args(object):
+    pass
+
+
+def reference_vcf_lines(results_by_chrom, ref_seqs, genotype, max_size=100000, min_size=30, report_readid=False, ignore_sequence=False):
+    """The reference's generate_output (cuteSV_genotype.py:242-467) + the SVID loop of main_ctrl
+    (cuteSV:1208-1237) on in-memory rows, with pysam.FastaFile stubbed by `ref_seqs`."""
+    import copy
+    m = modules()
+    pys = sys.modules["pysam"]
+
+    class FastaFile(object):
+        def __init__(self, path):
+            pass
+
+        def fetch(self, chrom):
+            return ref_seqs[chrom]
+
+        def close(self):
+            pass
+    pys.FastaFile = FastaFile
+    args = _Args()
+    args.genotype, args.max_size, args.min_size = genotype, max_size, min_size
+    args.report_readid, args.ignore_sequence = report_readid, ignore_sequence
+    lines = []
+    svid = {"INS": 0, "DEL": 0, "BND": 0, "DUP": 0, "INV": 0}
+    with tempfile.TemporaryDirectory() as d:
+        tmp = d + "/"
+        os.mkdir(tmp + "results")
+        for chrom in sorted(results_by_chrom):
+            m["genotype"].generate_output(args, copy.deepcopy(results_by_chrom[chrom]), "ref.fa", chrom, tmp)
+        for chrom in sorted(results_by_chrom):
+            with open("%sresults/%s.pickle" % (tmp, chrom), "rb") as f:
+                while True:
+                    try:
+                        for svtype, line in pickle.load(f):
+                            lines.append(line.replace("<SVID>", str(svid[svtype])))
+                            svid[svtype] += 1
+                    except EOFError:
+                        break
+    return lines
