@@ -1,0 +1,311 @@
+"""`cuteSV <bam> <ref> <vcf> <work_dir> [flags]` -- the reference's CLI shell around the B200 path.
+
+Same positionals, flags, defaults and pre-flight errors as the reference (cuteSV_Description.py:53-263,
+cuteSV:992-1011).  BAM decoding stays with pysam (north star); everything between decoded records and
+candidate rows runs through the C-ABI: csv_extract (replaces Pool#1), csv_cluster (Pool#2 + Pool#3).
+VCF formatting is host code (cutesv_b200/vcf.py).
+"""
+import argparse
+import logging
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import _abi, packing, rows, vcf, workdir
+
+VERSION = vcf.VERSION
+PACKET_READS = 50000
+
+
+def build_parser():
+    p = argparse.ArgumentParser(prog="cuteSV", description="Long-read SV detection (cuteSV hot path on B200).",
+                                formatter_class=argparse.RawDescriptionHelpFormatter)
+    p.add_argument("--version", "-v", action="version", version="%(prog)s {version}".format(version=VERSION))
+    p.add_argument("input", metavar="[BAM]", type=str, help="Sorted .bam file from NGMLR or Minimap2.")
+    p.add_argument("reference", type=str, help="The reference genome in fasta format.")
+    p.add_argument("output", type=str, help="Output VCF format file.")
+    p.add_argument("work_dir", type=str, help="Work-directory for distributed jobs")
+    p.add_argument("-t", "--threads", default=16, type=int)
+    p.add_argument("-b", "--batches", default=10000000, type=int)
+    p.add_argument("-S", "--sample", default="NULL", type=str)
+    p.add_argument("--retain_work_dir", action="store_true")
+    p.add_argument("--write_old_sigs", action="store_true")
+    p.add_argument("--report_readid", action="store_true")
+    p.add_argument("--ignore_sequence", action="store_true")
+    g = p.add_argument_group("Collection of SV signatures")
+    g.add_argument("-p", "--max_split_parts", default=7, type=int)
+    g.add_argument("-q", "--min_mapq", default=20, type=int)
+    g.add_argument("-r", "--min_read_len", default=500, type=int)
+    g.add_argument("-md", "--merge_del_threshold", default=0, type=int)
+    g.add_argument("-mi", "--merge_ins_threshold", default=100, type=int)
+    g.add_argument("-include_bed", default=None, type=str)
+    g = p.add_argument_group("Generation of SV clusters")
+    g.add_argument("-s", "--min_support", default=10, type=int)
+    g.add_argument("-l", "--min_size", default=30, type=int)
+    g.add_argument("-L", "--max_size", default=100000, type=int)
+    g.add_argument("-sl", "--min_siglength", default=10, type=int)
+    g = p.add_argument_group("Computing genotypes")
+    g.add_argument("--genotype", action="store_true")
+    g.add_argument("--gt_round", default=500, type=int)
+    g.add_argument("--read_range", default=1000, type=int)
+    g = p.add_argument_group("Force calling")
+    g.add_argument("-Ivcf", default=None, type=str)
+    g = p.add_argument_group("Advanced")
+    g.add_argument("--max_cluster_bias_INS", default=100, type=int)
+    g.add_argument("--diff_ratio_merging_INS", default=0.3, type=float)
+    g.add_argument("--max_cluster_bias_DEL", default=200, type=int)
+    g.add_argument("--diff_ratio_merging_DEL", default=0.5, type=float)
+    g.add_argument("--max_cluster_bias_INV", default=500, type=int)
+    g.add_argument("--max_cluster_bias_DUP", default=500, type=int)
+    g.add_argument("--max_cluster_bias_TRA", default=50, type=int)
+    g.add_argument("--diff_ratio_filtering_TRA", default=0.6, type=float)
+    g.add_argument("--remain_reads_ratio", default=1.0, type=float)
+    return p
+
+
+def params_from_args(a):
+    return _abi.default_params(
+        min_support=a.min_support, min_size=a.min_size, max_size=a.max_size, bias_del=a.max_cluster_bias_DEL,
+        bias_ins=a.max_cluster_bias_INS, bias_inv=a.max_cluster_bias_INV, bias_dup=a.max_cluster_bias_DUP,
+        bias_tra=a.max_cluster_bias_TRA, genotype=1 if a.genotype else 0, gt_round=a.gt_round, ratio_del=a.diff_ratio_merging_DEL,
+        ratio_ins=a.diff_ratio_merging_INS, ratio_tra=a.diff_ratio_filtering_TRA, remain_reads_ratio=a.remain_reads_ratio,
+        min_mapq=a.min_mapq, max_split_parts=a.max_split_parts, min_read_len=a.min_read_len, min_siglength=a.min_siglength,
+        merge_del_threshold=a.merge_del_threshold, merge_ins_threshold=a.merge_ins_threshold)
+
+
+def task_windows(ref_stats, get_len, threads, batches):
+    """Genome windows exactly like cuteSV:1018-1044 (coverage-balanced, float bounds included)."""
+    total_mapped = sum(i[1] for i in ref_stats)
+    mapped_unit = total_mapped / threads / 10
+    tasks, contig_info = [], []
+    for i in ref_stats:
+        n = get_len(i[0])
+        contig_info.append([i[0], n])
+        batch = batches if (total_mapped == 0 or i[1] <= mapped_unit) else n / (int(i[1] / mapped_unit) + 1)
+        if n < batch:
+            tasks.append([i[0], 0, n])
+        else:
+            pos = 0
+            for _ in range(int(n / batch)):
+                tasks.append([i[0], pos, pos + batch])
+                pos += batch
+            if pos < n:
+                tasks.append([i[0], pos, n])
+    return tasks, contig_info
+
+
+def load_bed(bed_file, tasks):
+    """-include_bed: regions padded by 1000 bp, assigned to windows (cuteSV_genotype.py:704-726)."""
+    if bed_file is None:
+        return None
+    regions = {}
+    with open(bed_file) as f:
+        for line in f:
+            s = line.strip().split("\t")
+            regions.setdefault(s[0], []).append((int(s[1]) - 1000, int(s[2]) + 1000))
+    out = [[] for _ in tasks]
+    for chrom in regions:
+        regions[chrom].sort()
+        for item in regions[chrom]:
+            for i, t in enumerate(tasks):
+                if chrom == t[0] and ((t[1] <= item[0] and t[2] > item[0]) or item[0] <= t[1] < item[1]):
+                    out[i].append(item)
+    return out
+
+
+class _Accumulator(object):
+    """Extracted signature columns / reads rows of all packets (host), provisional read ids."""
+
+    def __init__(self):
+        self.cols = {t: {k: [] for k in ("chrom", "a", "b", "read_id", "c")} for t in _abi.TYPE_NAMES}
+        self.ins_seq = []
+        self.rows = {k: [] for k in ("chrom", "start", "end", "read_id", "is_primary")}
+        self.name_id = {}
+        self.names = []
+
+    def rid(self, name):
+        i = self.name_id.get(name)
+        if i is None:
+            i = len(self.names)
+            self.name_id[name] = i
+            self.names.append(name)
+        return i
+
+    def add(self, ex, reads, want_seq):
+        for t in _abi.TYPE_NAMES:
+            for k in ("chrom", "a", "b", "read_id", "c"):
+                self.cols[t][k].append(ex["sigs"][t][k])
+        s = ex["sigs"]["INS"]
+        for i in range(len(s["chrom"])):
+            self.ins_seq.append(packing.ins_sequence(ex["pieces"], int(ex["piece_off"][i]), int(ex["piece_cnt"][i]),
+                                                     lambda rec: reads[rec].query_sequence) if want_seq else "")
+        for k in self.rows:
+            self.rows[k].append(ex["rows"][k])
+
+    def finish(self):
+        """Concatenate and turn provisional read ids into ranks in Python string order."""
+        order = sorted(range(len(self.names)), key=lambda i: self.names[i])
+        rank = np.zeros(max(len(order), 1), dtype=np.int32)
+        rank[np.array(order, dtype=np.int64)] = np.arange(len(order), dtype=np.int32)
+        sorted_names = [self.names[i] for i in order]
+        sigs = {}
+        for t in _abi.TYPE_NAMES:
+            c = {k: (np.concatenate(v) if v else np.zeros(0, np.int32)) for k, v in self.cols[t].items()}
+            c["read_id"] = rank[c["read_id"]] if len(c["read_id"]) else c["read_id"]
+            if t in ("DEL", "DUP"):
+                c["c"] = None
+            sigs[t] = c
+        r = {k: (np.concatenate(v) if v else np.zeros(0, np.uint8 if k == "is_primary" else np.int32)) for k, v in self.rows.items()}
+        r["read_id"] = rank[r["read_id"]] if len(r["read_id"]) else r["read_id"]
+        return sigs, r, sorted_names
+
+
+def main_ctrl(args, argv, engine=None):
+    tmp = args.work_dir if args.work_dir[-1] == "/" else args.work_dir + "/"
+    if args.Ivcf is not None:
+        raise ValueError("The force calling module has been disabled, please install cuteFC "
+                         "(https://github.com/Meltpinkg/cuteFC) to achieve SV force calling/regenotyping.")
+    if not os.path.isfile(args.reference):
+        raise FileNotFoundError("[Errno 2] No such file: '%s'" % args.reference)
+    if not os.path.exists(args.work_dir):
+        raise FileNotFoundError("[Errno 2] No such directory: '%s'" % args.work_dir)
+    if os.path.isdir("%sresults" % tmp):
+        raise FileExistsError("[Errno 2] Directory exists: '%sresults'" % tmp)
+    for t in workdir.TYPES:
+        for ext in (".sigs", ".pickle"):
+            if os.path.exists(tmp + t + ext):
+                raise FileExistsError("[Errno 2] File exists: '%s'" % (tmp + t + ext))
+    try:
+        import pysam
+    except ImportError:
+        raise RuntimeError("pysam is required to decode the BAM (it is the only part of the path that stays on pysam)")
+    from .engine import Engine
+    sam = pysam.AlignmentFile(args.input, reference_filename=args.reference)
+    stats = sam.get_index_statistics()
+    logging.info("The total number of chromsomes: %d" % len(stats))
+    tasks, contig_info = task_windows(stats, sam.get_reference_length, args.threads, args.batches)
+    bed = load_bed(args.include_bed, tasks)
+    chrom_names = sorted(c[0] for c in contig_info)
+    chrom_id = {n: i for i, n in enumerate(chrom_names)}
+    lens = {c[0]: c[1] for c in contig_info}
+    params = params_from_args(args)
+    eng = engine if engine is not None else Engine(int(os.environ.get("CUTESV_B200_DEVICE", "0")))
+    eng.set_params(params)
+    eng.set_contigs(np.array([lens[n] for n in chrom_names], dtype=np.int64))
+    acc = _Accumulator()
+    want_seq = not args.ignore_sequence
+
+    def flush(packet):
+        if not packet:
+            return
+        pk = packing.pack_alignments(packet, chrom_id, _NameIds(acc))
+        eng.extract(pk)
+        acc.add(eng.fetch_extracted(), packet, want_seq)
+
+    for i, task in enumerate(tasks):
+        packet = []
+        regions = None if bed is None else bed[i]
+        for read in sam.fetch(task[0], task[1], task[2]):
+            if read.flag == 256 or read.flag == 272:  # cuteSV:711
+                continue
+            if regions is not None and not any(not (read.reference_end <= r[0] or read.reference_start >= r[1]) for r in regions):
+                continue
+            if not read.reference_start >= task[1]:    # window ownership, cuteSV:725
+                continue
+            packet.append(read)
+            if len(packet) >= PACKET_READS:
+                flush(packet)
+                packet = []
+        flush(packet)
+        logging.info("Finished %s:%d-%d." % (task[0], task[1], task[2]))
+    logging.info("Rebuilding signatures of structural variants.")
+    sigs, reads_cols, read_names = acc.finish()
+    logging.info("Clustering structural variants.")
+    cands, genos, names = eng.cluster(sigs, reads_cols)
+    got = rows.records_to_rows(cands, genos, names, chrom_names, lambda k: read_names[k], lambda k: acc.ins_seq[k], bool(args.genotype))
+    results, tra_rows = {}, []
+    for t in ("DEL", "INS", "INV", "DUP", "TRA"):  # submission order of the reference, cuteSV:1116-1199
+        for (tt, chrom), r in got.items():
+            if tt == t:
+                results.setdefault(chrom, []).extend(r)
+                if t == "TRA":
+                    tra_rows.extend(r)
+    if args.genotype and tra_rows:  # TRA genotypes need the BAM (resolveTRA.py:260-309): completed on the host
+        from . import cuteSV_resolveTRA
+        for r in tra_rows:
+            ids = set(r[11].split(",")) if r[11] else set()
+            dv, dr, gt, gl, gq, qual = cuteSV_resolveTRA.call_gt(args.input, int(r[2]), int(r[4]), r[0], r[3], ids,
+                                                                 args.max_cluster_bias_TRA, args.gt_round)
+            r[6], r[7], r[8], r[9], r[10] = str(dr), str(gt), str(gl), str(gq), str(qual)
+    logging.info("Writing to your output file.")
+    reference = vcf.read_fasta(args.reference)
+    opts = dict(genotype=args.genotype, max_size=args.max_size, min_size=args.min_size, report_readid=args.report_readid,
+                ignore_sequence=args.ignore_sequence)
+    vcf.write_vcf(args.output, results, reference, contig_info, args.sample, argv, opts)
+    if args.retain_work_dir:
+        _write_workdir(tmp, sigs, reads_cols, chrom_names, read_names, acc.ins_seq, args.write_old_sigs)
+    sam.close()
+    return results
+
+
+class _NameIds(object):
+    """dict-like: read name -> provisional id (first-seen order); ranks are assigned at the end."""
+
+    def __init__(self, acc):
+        self.acc = acc
+
+    def __getitem__(self, name):
+        return self.acc.rid(name)
+
+
+def _write_workdir(tmp, sigs, reads_cols, chrom_names, read_names, ins_seq, write_old_sigs):
+    """--retain_work_dir: the reference's <TYPE>.pickle / sigindex.pickle layout (cuteSV:817-857)."""
+    tuples = {}
+    s = sigs["DEL"]
+    tuples["DEL"] = [(int(s["a"][i]), int(s["b"][i]), read_names[int(s["read_id"][i])], "DEL", chrom_names[int(s["chrom"][i])])
+                     for i in range(len(s["chrom"]))]
+    s = sigs["INS"]
+    tuples["INS"] = [((int(s["a"][i]) // 2 if int(s["a"][i]) % 2 == 0 else int(s["a"][i]) / 2), int(s["b"][i]), read_names[int(s["read_id"][i])],
+                      ins_seq[i], "INS", chrom_names[int(s["chrom"][i])]) for i in range(len(s["chrom"]))]
+    s = sigs["DUP"]
+    tuples["DUP"] = [(int(s["a"][i]), int(s["b"][i]), read_names[int(s["read_id"][i])], "DUP", chrom_names[int(s["chrom"][i])])
+                     for i in range(len(s["chrom"]))]
+    s = sigs["INV"]
+    tuples["INV"] = [("++" if int(s["c"][i]) == 0 else "--", int(s["a"][i]), int(s["b"][i]), read_names[int(s["read_id"][i])], "INV",
+                      chrom_names[int(s["chrom"][i])]) for i in range(len(s["chrom"]))]
+    s = sigs["TRA"]
+    tuples["TRA"] = [("ABCD"[int(s["c"][i]) & 3], int(s["a"][i]), chrom_names[int(s["c"][i]) >> 2], int(s["b"][i]),
+                      read_names[int(s["read_id"][i])], "TRA", chrom_names[int(s["chrom"][i])]) for i in range(len(s["chrom"]))]
+    r = reads_cols
+    tuples["reads"] = [(int(r["start"][i]), int(r["end"][i]), int(r["is_primary"][i]), read_names[int(r["read_id"][i])],
+                        chrom_names[int(r["chrom"][i])]) for i in range(len(r["chrom"]))]
+    workdir.write_workdir(tmp, tuples)
+    if write_old_sigs:  # legacy text dumps, cuteSV:766-816
+        fmt = {"DEL": lambda e: "%s\t%s\t%d\t%d\t%s\n" % (e[-2], e[-1], e[0], e[1], e[2]),
+               "INS": lambda e: "%s\t%s\t%d\t%d\t%s\t%s\n" % (e[-2], e[-1], e[0], e[1], e[2], e[3]),
+               "DUP": lambda e: "%s\t%s\t%d\t%d\t%s\n" % (e[-2], e[-1], e[0], e[1], e[2]),
+               "INV": lambda e: "%s\t%s\t%s\t%d\t%d\t%s\n" % (e[-2], e[-1], e[0], e[1], e[2], e[3]),
+               "TRA": lambda e: "%s\t%s\t%s\t%d\t%s\t%d\t%s\n" % (e[-2], e[-1], e[0], e[1], e[2], e[3], e[4])}
+        for t, f in fmt.items():
+            with open("%s/%s.sigs" % (tmp, t), "w") as fh:
+                for e in sorted(set(tuples[t]), key=workdir.sort_key(t)):
+                    fh.write(f(e))
+
+
+def setup_logging():
+    logging.basicConfig(stream=sys.stderr, level=logging.INFO, format="%(asctime)s [%(levelname)s] %(message)s")
+    logging.info("Running %s" % " ".join(sys.argv))
+
+
+def run(argv):
+    args = build_parser().parse_args(argv)
+    setup_logging()
+    t0 = time.time()
+    main_ctrl(args, argv)
+    logging.info("Finished in %0.2f seconds." % (time.time() - t0))
+
+
+if __name__ == "__main__":
+    run(sys.argv[1:])

@@ -438,3 +438,91 @@ def synth_alignments(seed, n_reads=200, n_contigs=3, with_seq=True):
         r.tags = tags
         reads.append(r)
     return reads, names, lens
+
+
+def synth_bam_dataset(seed=1, n_contigs=2, contig_len=120000, coverage=22, read_len=(2500, 7000)):
+    """A small coherent long-read dataset for the CLI plumbing test (BASELINE.json config 1 in
+    spirit): reads tile the contigs; planted DEL / INS loci appear in the CIGAR of the reads that
+    span them (position / length jitter), TRA loci as split reads with SA tags.  Returns
+    dict(contigs=[(name, len)], reads=[SynthRead]), fasta {name: seq}."""
+    rng = np.random.default_rng(seed)
+    names = ["chrA", "chrB", "chrC"][:n_contigs]
+    loci = []
+    for ci, nm in enumerate(names):
+        pos = 6000
+        while pos < contig_len - 8000:
+            kind = rng.choice(["DEL", "INS", "DEL", "INS", "TRA"]) if ci == 0 else rng.choice(["DEL", "INS"])
+            loci.append((nm, int(pos), str(kind), int(rng.integers(60, 600)), bool(rng.random() < 0.5)))
+            pos += int(rng.integers(5000, 9000))
+    reads = []
+    rid = 0
+    for nm in names:
+        n_reads = int(coverage * contig_len / ((read_len[0] + read_len[1]) / 2))
+        starts = np.sort(rng.integers(0, contig_len - read_len[1] - 1000, n_reads))
+        for st in starts:
+            L = int(rng.integers(read_len[0], read_len[1]))
+            r = SynthRead()
+            r.query_name = read_name(rid)
+            rid += 1
+            r.flag = 0 if rng.random() < 0.5 else 16
+            r.mapq = int(rng.choice([60, 60, 60, 30, 10]))
+            r.reference_name = nm
+            r.reference_start = int(st)
+            ops = []
+            ref = int(st)
+            end = int(st) + L
+            tags = [("NM", 5)]
+            tra_hit = None
+            here = [l for l in loci if l[0] == nm and ref + 300 < l[1] < end - 300]
+            for (_, lp, kind, ln, hom) in here:
+                if not hom and rng.random() < 0.5:
+                    continue
+                if kind == "TRA":
+                    tra_hit = (lp, ln)
+                    continue
+                lp2 = lp + int(rng.integers(-8, 9))
+                if lp2 <= ref + 20:
+                    continue
+                seg = lp2 - ref
+                while seg > 0:  # match run with small noise indels
+                    m = int(min(seg, rng.integers(80, 400)))
+                    ops.append((0, m))
+                    seg -= m
+                    ref += m
+                    if seg > 10 and rng.random() < 0.3:
+                        nl = int(rng.integers(1, 9))
+                        if rng.random() < 0.5:
+                            ops.append((1, nl))
+                        else:
+                            ops.append((2, nl))
+                            ref += nl
+                            seg -= nl
+                ln2 = max(int(ln * rng.normal(1.0, 0.03)), 30)
+                if kind == "DEL":
+                    ops.append((2, ln2))
+                    ref += ln2
+                else:
+                    ops.append((1, ln2))
+            if tra_hit is not None:
+                end = tra_hit[0] + int(rng.integers(-5, 6))
+            if end > ref:
+                ops.append((0, end - ref))
+                ref = end
+            clip = 0
+            if tra_hit is not None:  # split read: the tail maps to the last contig
+                clip = int(rng.integers(800, 2000))
+                ops.append((4, clip))
+            qlen = sum(l for o, l in ops if o in (0, 1, 4, 7, 8))
+            if tra_hit is not None:
+                tgt = 20000 + tra_hit[1] * 10 + int(rng.integers(-5, 6))
+                tags.append(("SA", "%s,%d,+,%dS%dM,60,3;" % (names[-1], tgt, qlen - clip, clip)))
+                r.flag = 0
+            r.cigartuples = ops
+            r.cigar = ops
+            r.query_length = qlen
+            r.reference_end = ref
+            r.query_sequence = "".join(rng.choice(list("ACGT"), qlen))
+            r.tags = tags
+            reads.append(r)
+    fasta = {nm: "".join(rng.choice(list("ACGT"), contig_len + 10)) for nm in names}
+    return dict(contigs=[(nm, contig_len) for nm in names], reads=reads), fasta

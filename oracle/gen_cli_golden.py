@@ -1,0 +1,48 @@
+"""Runs the REAL reference CLI core (main_ctrl, cuteSV:992-1248) end to end on the synthetic BAM data
+set through the test-only fake pysam, and commits the VCF body as tests/golden/cli_dataset1.json.
+Authoring container only:  python -m oracle.gen_cli_golden"""
+import json
+import os
+import pickle
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "fake_pysam"))
+
+FLAGS = ["--genotype", "-s", "5", "--threads", "4", "--max_cluster_bias_INS", "100", "--diff_ratio_merging_INS", "0.3",
+         "--max_cluster_bias_DEL", "100", "--diff_ratio_merging_DEL", "0.3"]
+
+
+def materialise(d, seed=1):
+    from cutesv_b200 import synth
+    ds, fasta = synth.synth_bam_dataset(seed)
+    bam = os.path.join(d, "x.bam")
+    with open(bam, "wb") as f:
+        pickle.dump(ds, f)
+    fa = os.path.join(d, "ref.fa")
+    with open(fa, "w") as f:
+        f.write("".join(">%s\n%s\n" % (k, v) for k, v in fasta.items()))
+    wd = os.path.join(d, "wd")
+    os.mkdir(wd)
+    return bam, fa, os.path.join(d, "out.vcf"), wd
+
+
+def main():
+    import pysam  # noqa: F401  (the fake one, first on sys.path)
+    from oracle import ref_harness
+    m = ref_harness.modules()
+    from cuteSV.cuteSV_Description import parseArgs
+    d = tempfile.mkdtemp()
+    bam, fa, out, wd = materialise(d)
+    argv = [bam, fa, out, wd] + FLAGS
+    m["main"].main_ctrl(parseArgs(argv), argv)
+    lines = [l for l in open(out) if not l.startswith("##")]
+    with open(os.path.join(ROOT, "tests", "golden", "cli_dataset1.json"), "w") as f:
+        json.dump(dict(flags=FLAGS, lines=lines), f)
+    print(len(lines) - 1, "records")
+
+
+if __name__ == "__main__":
+    main()

@@ -76,6 +76,7 @@ def modules():
         loader = importlib.machinery.SourceFileLoader("cutesv_ref_main", os.path.join(REF_SRC, "cuteSV", "cuteSV"))
         spec = importlib.util.spec_from_loader("cutesv_ref_main", loader)
         main = importlib.util.module_from_spec(spec)
+        sys.modules["cutesv_ref_main"] = main  # multiprocessing pickles its functions by module name
         loader.exec_module(main)
         _mods.update(main=main, indel=cuteSV_resolveINDEL, dup=cuteSV_resolveDUP, inv=cuteSV_resolveINV,
                      tra=cuteSV_resolveTRA, genotype=cuteSV_genotype)
