@@ -22,13 +22,13 @@ def test_defaults_and_flags_match_reference():
 
 
 def test_task_windows_float_bounds():
-    stats = [("c1", 1000, 0, 1000), ("c2", 10, 0, 10)]
+    stats = [("c1", 1000, 0, 1000), ("c2", 1, 0, 1)]
     lens = {"c1": 25000000, "c2": 5000}
     tasks, info = cli.task_windows(stats, lambda n: lens[n], 16, 10000000)
     assert info == [["c1", 25000000], ["c2", 5000]]
     assert tasks[-1] == ["c2", 0, 5000]
     c1 = [t for t in tasks if t[0] == "c1"]
-    unit = 1010 / 16 / 10
+    unit = 1001 / 16 / 10
     batch = 25000000 / (int(1000 / unit) + 1)   # coverage-balanced float window size, cuteSV:1034
     assert c1[0][1] == 0 and c1[0][2] == batch
     for x, y in zip(c1, c1[1:]):
