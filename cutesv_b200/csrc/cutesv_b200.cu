@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -106,6 +107,7 @@ struct csv_ctx {
     // sort workspace
     DBuf keys_a, keys_b, vals_a, vals_b, hist, lb_status, tickets, bkt, bkt_flags;
     bool prefilter_enabled = true;
+    int64_t pair_cap_override = 0;
     uint32_t gen = 1;
     int ticket_next = 0;
     SmallWork small;
@@ -251,6 +253,8 @@ extern "C" int csv_create(int device, void* stream, csv_ctx** out) {
         c->own_stream = true;
     }
     csv_default_params(&c->P);
+    if (const char* e = getenv("CUTESV_B200_PAIR_CAP")) c->pair_cap_override = atoll(e);
+    if (const char* e = getenv("CUTESV_B200_NO_PREFILTER")) c->prefilter_enabled = atoi(e) == 0;
     for (int s = 0; s < CSV_ST_COUNT; s++) c->stage_ms[s] = 0.f;
     cudaError_t e3 = cudaMallocHost((void**)&c->h_counters, sizeof(Counters));
     if (e3 != cudaSuccess) { delete c; return set_err(CSV_E_CUDA, "cudaMallocHost: %s", cudaGetErrorString(e3)); }
@@ -740,7 +744,8 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
             LAUNCH(c, (k_windows<1>), grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
             if (c->n_reads > 0) {
                 PairBuf PB;
-                PB.cap = (uint32_t)std::min<int64_t>(2 * c->n_reads + (1 << 20), (int64_t)1 << 30);
+                PB.cap = (uint32_t)std::min<int64_t>(4 * c->n_reads + (1 << 20), (int64_t)1 << 30);
+                if (c->pair_cap_override > 0) PB.cap = (uint32_t)c->pair_cap_override;  // tests: force the overflow path
                 CU(c->pairs.ensure((size_t)PB.cap * sizeof(uint2)));
                 PB.pairs = c->pairs.as<uint2>();
                 PB.count = &ctr->n_windows;

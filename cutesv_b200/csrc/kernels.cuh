@@ -536,12 +536,14 @@ __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const
         for (int j = 0; j < ITEMS; j++) {
             if (!cnt[j]) continue;
             const int64_t r = base + j * 256 + threadIdx.x;
-            if ((uint64_t)o + cnt[j] <= PB.cap) {
-                for (uint32_t k = 0; k < cnt[j]; k++) PB.pairs[o + k] = make_uint2((uint32_t)r, w[j] + k);
-            } else {  // pair buffer full: test inline (correct, just slower)
+            // slots below the capacity go to the pair buffer (every reserved slot < cap MUST be written:
+            // k_pairs_test consumes [0, min(count, cap))); the rest is tested inline (correct, just slower)
+            uint32_t k = 0;
+            for (; k < cnt[j] && (uint64_t)o + k < PB.cap; k++) PB.pairs[o + k] = make_uint2((uint32_t)r, w[j] + k);
+            if (k < cnt[j]) {
                 const uint64_t off = G.ct.off[ch[j]];
                 const int32_t rid = r_id[r];
-                for (uint32_t k = 0; k < cnt[j]; k++)
+                for (; k < cnt[j]; k++)
                     test_pair(G, off + (uint64_t)(uint32_t)st[j], off + (uint64_t)(uint32_t)en[j], rid, w[j] + k);
             }
             o += cnt[j];

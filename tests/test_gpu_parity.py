@@ -72,3 +72,23 @@ def test_cal_gl_full_domain(engine):
         ref = oracle_lib.cal_gl(int(c0[i]), int(c1[i]))
         g = got[i]
         assert (g["gt"], tuple(g["pl"]), g["gq"], g["qual"]) == (ref["gt"], tuple(ref["pl"]), ref["gq"], ref["qual"]), (c0[i], c1[i])
+
+
+def test_pair_buffer_overflow_and_no_prefilter(monkeypatch):
+    """Debug knobs: a tiny (read, window) pair buffer forces the inline-test overflow path of the reads
+    pass; disabling the density filter sorts every signature.  Results must not change."""
+    from cutesv_b200.engine import Engine
+    cfg = synth.make_config(2, 0.05)
+    p = _abi.default_params(**cfg["params"])
+    ref = oracle_lib.cluster(p, cfg["lens"], cfg["sigs"], cfg["reads"], n_threads=8)
+    for env in ({"CUTESV_B200_PAIR_CAP": "1000"}, {"CUTESV_B200_NO_PREFILTER": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = Engine(0, params=p, contig_lens=cfg["lens"])
+        for _ in range(2):  # the second run sees the first run's stale buffers
+            got = e.cluster(cfg["sigs"], cfg["reads"])
+            d = compare_records.diff_records(ref, got)
+            assert not d, "\n".join(d[:3])
+        e.close()
+        for k in env:
+            monkeypatch.delenv(k)
