@@ -49,34 +49,59 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(ReadView R, const uint32
             InsPiece open_pieces[MAX_OPEN_PIECES];
             int32_t ref = ref_start;
             int64_t q = -(int64_t)hard_l;
-            for (int64_t base = c_lo; base < c_hi; base += 32) {
-                const int64_t i = base + lane;
-                const uint32_t cg = i < c_hi ? cigar[i] : 0u;
-                const int op = (i < c_hi) ? (int)(cg & 15) : OP_P;
-                const int32_t len = (i < c_hi) ? (int32_t)(cg >> 4) : 0;
-                const int32_t radv = op_ref_change(op) ? len : 0;     // cuteSV:633-643
-                const int32_t qadv = (op != OP_D) ? len : 0;           // cuteSV:631-632
-                int32_t ir = radv, iq = qadv;
+            // 128 CIGAR ops per warp iteration: every lane owns 4 consecutive ops, so one warp scan
+            // (5 shuffle steps per offset) is amortised over 128 ops
+            for (int64_t base = c_lo; base < c_hi; base += 128) {
+                int op[4];
+                int32_t len[4], radv[4], qadv[4];
+                int32_t r_tot = 0, q_tot = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int64_t i = base + lane * 4 + j;
+                    const uint32_t cg = i < c_hi ? cigar[i] : (uint32_t)OP_P;
+                    op[j] = (int)(cg & 15);
+                    len[j] = (int32_t)(cg >> 4);
+                    radv[j] = op_ref_change(op[j]) ? len[j] : 0;     // cuteSV:633-643
+                    qadv[j] = (op[j] != OP_D) ? len[j] : 0;           // cuteSV:631-632
+                    r_tot += radv[j];
+                    q_tot += qadv[j];
+                }
+                int32_t ir = r_tot, iq = q_tot;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const int32_t yr = __shfl_up_sync(0xffffffffu, ir, d);
                     const int32_t yq = __shfl_up_sync(0xffffffffu, iq, d);
                     if (lane >= d) { ir += yr; iq += yq; }
                 }
-                const int32_t sig_start = ref + ir - radv;
-                const int64_t shift_after = q + iq;
-                const bool qual = len >= P.min_siglength && (op == OP_I || op == OP_D) && i < c_hi;
-                uint32_t mask = __ballot_sync(0xffffffffu, qual);
-                while (mask) {
-                    const int j = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int v_op = __shfl_sync(0xffffffffu, op, j);
-                    const int32_t v_len = __shfl_sync(0xffffffffu, len, j);
-                    const int32_t v_pos = __shfl_sync(0xffffffffu, sig_start, j);
-                    const int64_t v_shift = __shfl_sync(0xffffffffu, shift_after, j);
-                    if (lane == 0) {
-                        if (v_op == OP_D) push_del(O, RC, P, S, v_pos, v_len);
-                        else push_ins(O, RC, P, S, open_pieces, v_pos, v_len, v_shift - v_len, v_shift);
+                int32_t sig_start[4];
+                int64_t shift_after[4];
+                uint32_t qmask = 0;
+                int32_t run_r = ref + ir - r_tot;
+                int64_t run_q = q + iq - q_tot;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    sig_start[j] = run_r;
+                    run_r += radv[j];
+                    run_q += qadv[j];
+                    shift_after[j] = run_q;
+                    if (len[j] >= P.min_siglength && (op[j] == OP_I || op[j] == OP_D) && base + lane * 4 + j < c_hi) qmask |= 1u << j;
+                }
+                uint32_t lanes = __ballot_sync(0xffffffffu, qmask != 0);
+                while (lanes) {  // qualifying ops are rare (~2 per read): serial hand-over to lane 0, in read order
+                    const int L = __ffs(lanes) - 1;
+                    lanes &= lanes - 1;
+                    const uint32_t m4 = __shfl_sync(0xffffffffu, qmask, L);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (!(m4 >> j & 1u)) continue;
+                        const int v_op = __shfl_sync(0xffffffffu, op[j], L);
+                        const int32_t v_len = __shfl_sync(0xffffffffu, len[j], L);
+                        const int32_t v_pos = __shfl_sync(0xffffffffu, sig_start[j], L);
+                        const int64_t v_shift = __shfl_sync(0xffffffffu, shift_after[j], L);
+                        if (lane == 0) {
+                            if (v_op == OP_D) push_del(O, RC, P, S, v_pos, v_len);
+                            else push_ins(O, RC, P, S, open_pieces, v_pos, v_len, v_shift - v_len, v_shift);
+                        }
                     }
                 }
                 ref += __shfl_sync(0xffffffffu, ir, 31);

@@ -198,13 +198,25 @@ __global__ void k_indel_keys(const int32_t* __restrict__ chrom, const int32_t* _
 // 1.5 MB for hg19 and stays cache resident for the per-signature test.
 __global__ void __launch_bounds__(256) k_bucket_flags(const uint32_t* __restrict__ bkt, uint32_t n_buckets, int rb, uint32_t need,
                                                       uint32_t* __restrict__ flags) {
-    const uint32_t n_round = (n_buckets + 31) / 32 * 32;
-    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_round; b += gridDim.x * blockDim.x) {
-        uint32_t sum = 0;
-        if (b < n_buckets)
-            for (int k = -rb; k <= rb; k++) sum += bkt[(int64_t)b + k + BKT_PAD];
-        const uint32_t m = __ballot_sync(0xffffffffu, sum >= need);
-        if ((threadIdx.x & 31) == 0) flags[b >> 5] = m;
+    // every thread owns 16 consecutive buckets and slides the window sum along them (2 loads per
+    // bucket instead of 2*rb+1); lane pairs assemble one 32-bit flag word
+    constexpr int PER = 16;
+    const uint32_t n_words = (n_buckets + 31) / 32;
+    const uint32_t n_threads_needed = n_words * 2;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ((n_threads_needed + 31) / 32) * 32; t += gridDim.x * blockDim.x) {
+        uint32_t mask = 0;
+        if (t < n_threads_needed) {
+            const int64_t b0 = (int64_t)t * PER;
+            uint32_t sum = 0;
+            for (int k = -rb; k <= rb; k++) sum += bkt[b0 + k + BKT_PAD];
+#pragma unroll
+            for (int j = 0; j < PER; j++) {
+                if (b0 + j < n_buckets && sum >= need) mask |= 1u << j;
+                sum += bkt[b0 + j + 1 + rb + BKT_PAD] - bkt[b0 + j - rb + BKT_PAD];
+            }
+        }
+        const uint32_t other = __shfl_down_sync(0xffffffffu, mask, 1);
+        if ((threadIdx.x & 1) == 0 && t < n_threads_needed) flags[t >> 1] = mask | (other << 16);
     }
 }
 

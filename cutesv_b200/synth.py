@@ -526,3 +526,34 @@ def synth_bam_dataset(seed=1, n_contigs=2, contig_len=120000, coverage=22, read_
             reads.append(r)
     fasta = {nm: "".join(rng.choice(list("ACGT"), contig_len + 10)) for nm in names}
     return dict(contigs=[(nm, contig_len) for nm in names], reads=reads), fasta
+
+
+def synth_cigar_packet(n_reads, mean_indels=850, seed=5, n_contigs=25, sa_frac=0.0):
+    """Vectorised packed alignment packet (no Python objects) shaped like ONT reads: ~1 CIGAR op per
+    7 bp, M / small indel alternation, ~1 qualifying (>= 10 bp) insertion and deletion per read
+    (BASELINE.json config 5 stresses this CIGAR walk).  Returns a packing.pack_alignments()-style dict."""
+    rng = np.random.default_rng(seed)
+    names, lens = contigs(1.0, n_contigs)
+    k = np.maximum(rng.poisson(mean_indels, n_reads), 1).astype(np.int64)
+    n_ops = 2 * k + 1
+    off = np.concatenate([[0], np.cumsum(n_ops)])
+    T = int(off[-1])
+    idx_in_read = np.arange(T, dtype=np.int64) - np.repeat(off[:-1], n_ops)
+    is_m = (idx_in_read % 2) == 0
+    op = np.where(is_m, 0, np.where(rng.random(T) < 0.5, 1, 2)).astype(np.uint32)
+    ln = np.where(is_m, 1 + rng.geometric(1.0 / 12.0, T), 1 + rng.geometric(0.6, T)).astype(np.int64)
+    big = (~is_m) & (rng.random(T) < 2.2 / (2.0 * mean_indels))
+    ln[big] = 10 + rng.geometric(0.05, int(big.sum()))
+    cigar = ((ln.astype(np.uint32) << 4) | op).astype(np.uint32)
+    ref_adv = np.where(op != 1, ln, 0)
+    q_adv = np.where(op != 2, ln, 0)
+    span = np.add.reduceat(ref_adv, off[:-1])
+    qlen = np.add.reduceat(q_adv, off[:-1])
+    chrom = _pick_contig(rng, lens, n_reads)
+    start = (rng.random(n_reads) * np.maximum(lens[chrom] - span - 1, 1)).astype(np.int64)
+    out = dict(chrom=chrom.astype(np.int32), ref_start=start.astype(np.int32), ref_end=(start + span).astype(np.int32),
+               flag=np.where(rng.random(n_reads) < 0.5, 0, 16).astype(np.int32), mapq=np.full(n_reads, 60, np.int32),
+               query_len=qlen.astype(np.int32), read_id=np.arange(n_reads, dtype=np.int32), cigar_off=off.astype(np.int64),
+               sa_off=np.zeros(n_reads + 1, dtype=np.int64), cigar=cigar,
+               sa={k2: np.zeros(0, np.int32) for k2 in ("chrom", "pos0", "strand", "mapq", "first_clip", "last_clip", "ref_span")})
+    return out, names, lens
