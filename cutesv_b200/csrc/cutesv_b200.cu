@@ -531,7 +531,7 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
     const int rb = (int)((radius + (1u << BKT_SHIFT) - 1) >> BKT_SHIFT);  // neighbourhood radius in buckets (conservative)
     const bool prefilter = !k64 && c->prefilter_enabled && J.cp.min_support >= 3 && lambda < 0.8 * J.cp.min_support &&
                            n >= (1 << 16) && rb <= BKT_PAD;
-    const size_t n_bkt = (size_t)(total >> BKT_SHIFT) + 3 * BKT_PAD + 64;
+    const size_t n_bkt = (((size_t)(total >> BKT_SHIFT) + 4096) / 4096 + 1) * 4096 + 3 * BKT_PAD + 64;
     stage_begin(c, CSV_ST_KEYS);
     if (prefilter) {
         CU(c->bkt.ensure(n_bkt * 4));
@@ -541,7 +541,7 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
         uint32_t* n_pass = &ctr->n_dom[t];
         const uint32_t n_buckets = (uint32_t)(total >> BKT_SHIFT) + 1;
         CU(c->bkt_flags.ensure(((size_t)n_buckets / 32 + 2) * 4));
-        LAUNCH(c, k_bucket_flags, grid_for(c, n_buckets / 16 + 64, 256, 8), 256, 0, c->bkt.as<uint32_t>(), n_buckets, rb, (uint32_t)J.cp.min_support,
+        LAUNCH(c, k_bucket_flags, grid_for(c, n_buckets / 16 + 256, 256, 8), 256, 0, c->bkt.as<uint32_t>(), n_buckets, rb, (uint32_t)J.cp.min_support,
                c->bkt_flags.as<uint32_t>());
         LAUNCH(c, k_prefilter, grid_for(c, n, 2048, 8), 256, 0, c->keys_b.as<uint32_t>(), n, c->bkt_flags.as<uint32_t>(),
                c->keys_a.as<uint32_t>(), c->vals_a.as<uint32_t>(), n_pass);

@@ -198,25 +198,29 @@ __global__ void k_indel_keys(const int32_t* __restrict__ chrom, const int32_t* _
 // 1.5 MB for hg19 and stays cache resident for the per-signature test.
 __global__ void __launch_bounds__(256) k_bucket_flags(const uint32_t* __restrict__ bkt, uint32_t n_buckets, int rb, uint32_t need,
                                                       uint32_t* __restrict__ flags) {
-    // every thread owns 16 consecutive buckets and slides the window sum along them (2 loads per
-    // bucket instead of 2*rb+1); lane pairs assemble one 32-bit flag word
-    constexpr int PER = 16;
-    const uint32_t n_words = (n_buckets + 31) / 32;
-    const uint32_t n_threads_needed = n_words * 2;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ((n_threads_needed + 31) / 32) * 32; t += gridDim.x * blockDim.x) {
-        uint32_t mask = 0;
-        if (t < n_threads_needed) {
-            const int64_t b0 = (int64_t)t * PER;
-            uint32_t sum = 0;
-            for (int k = -rb; k <= rb; k++) sum += bkt[b0 + k + BKT_PAD];
+    // A CTA stages 4096 buckets (+ halo) in shared memory with coalesced loads; every thread then
+    // slides the window sum along its 16 consecutive buckets; lane pairs assemble a 32-bit word.
+    constexpr int PER = 16, TILE = 256 * PER;
+    __shared__ uint32_t s_b[(TILE + 2 * BKT_PAD + 8) * 17 / 16 + 8];
+    auto P = [](int i) { return i + (i >> 4); };  // +1 word per 16: threads stride 17 words -> no bank conflicts
+    const uint32_t n_tiles = (n_buckets + TILE - 1) / TILE;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t t0 = (int64_t)tile * TILE;                 // first bucket of the tile
+        // s_b[i] = bkt[t0 - rb + i + PAD], i in [0, TILE + 2*rb + 1)
+        for (int i = threadIdx.x; i < TILE + 2 * rb + 1; i += 256) s_b[P(i)] = bkt[t0 - rb + i + BKT_PAD];
+        __syncthreads();
+        const int l0 = threadIdx.x * PER;                        // local index of the thread's first bucket
+        uint32_t sum = 0, mask = 0;
+        for (int k = 0; k <= 2 * rb; k++) sum += s_b[P(l0 + k)];
 #pragma unroll
-            for (int j = 0; j < PER; j++) {
-                if (b0 + j < n_buckets && sum >= need) mask |= 1u << j;
-                sum += bkt[b0 + j + 1 + rb + BKT_PAD] - bkt[b0 + j - rb + BKT_PAD];
-            }
+        for (int j = 0; j < PER; j++) {
+            if (t0 + l0 + j < n_buckets && sum >= need) mask |= 1u << j;
+            sum += s_b[P(l0 + j + 2 * rb + 1)] - s_b[P(l0 + j)];
         }
         const uint32_t other = __shfl_down_sync(0xffffffffu, mask, 1);
-        if ((threadIdx.x & 1) == 0 && t < n_threads_needed) flags[t >> 1] = mask | (other << 16);
+        const int64_t word = (t0 + l0) >> 5;
+        if ((threadIdx.x & 1) == 0 && t0 + l0 < n_buckets) flags[word] = mask | (other << 16);
+        __syncthreads();
     }
 }
 
