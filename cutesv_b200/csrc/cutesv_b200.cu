@@ -506,7 +506,9 @@ static int run_segment_and_cluster(csv_ctx* c, TypeJob& J, int t, uint32_t kslot
     stage_begin(c, CSV_ST_CLUSTER);
     Emit E = make_emit(c);
     const size_t smem_warp = (size_t)(CL_THREADS / 32) * WARP_M * ARENA_PER_MAX + (CL_THREADS / 32) * 40 * 8;
-    LAUNCH(c, k_cluster_warp, c->n_sm * 3, CL_THREADS, smem_warp, J, E, ctr);
+    if (c->ticket_next >= 1024) return set_err(CSV_E_STATE, "ticket pool exhausted");
+    uint32_t* work = c->tickets.as<uint32_t>() + c->ticket_next++;  // zeroed per call
+    LAUNCH(c, k_cluster_warp, c->n_sm * 3, CL_THREADS, smem_warp, J, E, ctr, work);
     LAUNCH(c, (k_cluster_block<false>), c->n_sm, CL_THREADS, (size_t)BLOCK_M * ARENA_PER_MAX, J, E, ctr);
     LAUNCH(c, (k_cluster_block<true>), c->n_sm, CL_THREADS, 0, J, E, ctr);
     stage_end(c, CSV_ST_CLUSTER);

@@ -346,7 +346,7 @@ __device__ __forceinline__ int cluster_size_warp(const TypeJob& J, int64_t s, in
 }
 
 // one warp per kept cluster; clusters larger than WARP_M are deferred to the CTA kernel
-__global__ void __launch_bounds__(CL_THREADS) k_cluster_warp(TypeJob J, Emit E, Counters* ctr) {
+__global__ void __launch_bounds__(CL_THREADS) k_cluster_warp(TypeJob J, Emit E, Counters* ctr, uint32_t* work) {
     extern __shared__ __align__(16) char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int WARPS = CL_THREADS / 32;
@@ -355,7 +355,12 @@ __global__ void __launch_bounds__(CL_THREADS) k_cluster_warp(TypeJob J, Emit E, 
     const int64_t n = job_n(J);
     const uint32_t n_kept = ctr->n_kept[J.svtype];
     CudaTeam<32> tm;
-    for (uint32_t k = blockIdx.x * WARPS + warp; k < n_kept; k += gridDim.x * WARPS) {
+    // dynamic hand-out (one atomic per cluster): cluster costs vary, a static stride leaves a long tail
+    while (true) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(work, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_kept) break;
         const int64_t s = J.kept_start[k];
         const int m = cluster_size_warp(J, s, n, WARP_M);
         if (m > WARP_M) {
