@@ -135,8 +135,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "config2: synthetic 30x ONT WGS signature arrays, INS+DEL, --genotype", "scale": args.scale,
-                   "n_signatures": cfg["n_sigs"], "n_reads": int(len(cfg["reads"]["chrom"]))},
+        "config": {"workload": "config2: synthetic 30x ONT WGS signature arrays, resolution_INS + resolution_DEL, --genotype",
+                   "scale": args.scale, "n_signatures_per_gpu": cfg["n_sigs"], "n_reads_per_gpu": int(len(cfg["reads"]["chrom"])),
+                   "note": "CPU arm: rank 0 only, one genome-equivalent per step on all host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "full workload per step (oracle/cutesv_oracle.c, OpenMP over (type, contig))"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
