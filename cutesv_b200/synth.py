@@ -557,3 +557,90 @@ def synth_cigar_packet(n_reads, mean_indels=850, seed=5, n_contigs=25, sa_frac=0
                sa_off=np.zeros(n_reads + 1, dtype=np.int64), cigar=cigar,
                sa={k2: np.zeros(0, np.int32) for k2 in ("chrom", "pos0", "strand", "mapq", "first_clip", "last_clip", "ref_span")})
     return out, names, lens
+
+
+def synth_config1_dataset(loci, contig="22", contig_len=51304566, seed=20260924, reads_per_locus=15):
+    """BASELINE.json configs[0]: BED-driven chr22 INS+DEL, ~5k synthetic reads.
+    loci: [[kind, start, length], ...] (chr22 rows of the reference's simulation BEDs, committed as
+    tests/golden/sim_chr22_loci.json).  ~15 reads per locus, read length lognormal(median 9 kb, sigma 0.7)
+    clipped to [500, 200k], 50 % het / 50 % hom, CIGAR = M runs with small noise indels + the SV op
+    (+-15 bp position jitter, +-4 % length jitter), 10 % of the SVs expressed as an SA split instead of a
+    CIGAR op.  Returns (dict(contigs, reads), fasta_as_function)."""
+    rng = np.random.default_rng(seed)
+    reads = []
+    rid = 0
+    for kind, pos, ln in loci:
+        hom = rng.random() < 0.5
+        for _ in range(reads_per_locus):
+            carries = hom or rng.random() < 0.5
+            L = int(np.clip(rng.lognormal(np.log(9000.0), 0.7), 500, 200000))
+            left = int(rng.integers(int(0.1 * L), int(0.9 * L) + 1))
+            st = max(pos - left, 0)
+            r = SynthRead()
+            r.query_name = read_name(rid)
+            rid += 1
+            r.flag = 0 if rng.random() < 0.5 else 16
+            r.mapq = 60
+            r.reference_name = contig
+            r.reference_start = st
+            ops = []
+            tags = [("NM", 7)]
+            ref = st
+
+            def m_run(n, ref):
+                while n > 0:
+                    m = int(min(n, rng.integers(60, 300)))
+                    ops.append((0, m))
+                    n -= m
+                    ref += m
+                    if n > 12 and rng.random() < 0.10:
+                        nl = int(rng.integers(1, 10))
+                        if rng.random() < 0.5:
+                            ops.append((1, nl))
+                        else:
+                            ops.append((2, nl))
+                            ref += nl
+                            n -= nl
+                return ref
+            split = carries and rng.random() < 0.10
+            if carries and not split:
+                p2 = pos + int(rng.integers(-15, 16))
+                ref = m_run(max(p2 - ref, 1), ref)
+                l2 = max(int(round(ln * (1.0 + rng.uniform(-0.04, 0.04)))), 30)
+                if kind == "DEL":
+                    ops.append((2, l2))
+                    ref += l2
+                else:
+                    ops.append((1, l2))
+                ref = m_run(max(st + L - ref, 50), ref)
+            elif split:
+                # primary covers the left flank and soft-clips the rest; the SA entry maps the right flank
+                ref = m_run(max(pos - ref, 1), ref)
+                tail = max(L - (pos - st), 200)
+                l2 = max(int(round(ln * (1.0 + rng.uniform(-0.04, 0.04)))), 30)
+                ops.append((4, tail + (l2 if kind == "INS" else 0)))
+                qlen_now = sum(l for o, l in ops if o in (0, 1, 4, 7, 8))
+                sa_pos = pos + (l2 if kind == "DEL" else 0) + 1
+                strand = "+" if r.flag == 0 else "-"
+                lead = qlen_now - tail
+                sa_cig = ("%dS%dM" % (lead, tail)) if r.flag == 0 else ("%dM%dS" % (tail, lead))
+                tags.append(("SA", "%s,%d,%s,%s,60,5;" % (contig, sa_pos, strand, sa_cig)))
+                if r.flag == 16:  # reverse-strand records store the clip on the other side
+                    ops = [ops[-1]] + ops[:-1]
+            else:
+                ref = m_run(L, ref)
+            r.cigartuples = ops
+            r.cigar = ops
+            r.query_length = sum(l for o, l in ops if o in (0, 1, 4, 7, 8))
+            r.reference_end = st + sum(l for o, l in ops if o in (0, 2, 3, 7, 8))
+            r.query_sequence = "".join(rng.choice(list("ACGT"), r.query_length))
+            r.tags = tags
+            reads.append(r)
+    return dict(contigs=[(contig, contig_len)], reads=reads)
+
+
+def pseudo_fasta_line(contig, length, seed=3, width=60):
+    """Deterministic pseudo-random reference sequence, generated in chunks (used for the 51 Mb chr22 fixture)."""
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    return alphabet[rng.integers(0, 4, length)].tobytes().decode()

@@ -29,6 +29,26 @@ def materialise(d, seed=1):
     return bam, fa, os.path.join(d, "out.vcf"), wd
 
 
+# BASELINE.json configs[0]: BED-driven chr22 INS+DEL, ~5k reads, reference CPU path --threads 4, ONT preset
+FLAGS_CONFIG1 = ["--genotype", "-s", "5", "--threads", "4", "--max_cluster_bias_INS", "100", "--diff_ratio_merging_INS", "0.3",
+                 "--max_cluster_bias_DEL", "100", "--diff_ratio_merging_DEL", "0.3"]
+
+
+def materialise_config1(d):
+    from cutesv_b200 import synth
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "sim_chr22_loci.json")))
+    ds = synth.synth_config1_dataset(meta["loci"], meta["contig"], meta["contig_len"])
+    bam = os.path.join(d, "c1.bam")
+    with open(bam, "wb") as f:
+        pickle.dump(ds, f)
+    fa = os.path.join(d, "c1.fa")
+    with open(fa, "w") as f:
+        f.write(">%s\n%s\n" % (meta["contig"], synth.pseudo_fasta_line(meta["contig"], meta["contig_len"] + 16)))
+    wd = os.path.join(d, "wd1")
+    os.mkdir(wd)
+    return bam, fa, os.path.join(d, "c1.vcf"), wd
+
+
 def main():
     import pysam  # noqa: F401  (the fake one, first on sys.path)
     from oracle import ref_harness
@@ -42,6 +62,13 @@ def main():
     with open(os.path.join(ROOT, "tests", "golden", "cli_dataset1.json"), "w") as f:
         json.dump(dict(flags=FLAGS, lines=lines), f)
     print(len(lines) - 1, "records")
+    bam, fa, out, wd = materialise_config1(d)
+    argv = [bam, fa, out, wd] + FLAGS_CONFIG1
+    m["main"].main_ctrl(parseArgs(argv), argv)
+    lines = [l for l in open(out) if not l.startswith("##")]
+    with open(os.path.join(ROOT, "tests", "golden", "cli_config1.json"), "w") as f:
+        json.dump(dict(flags=FLAGS_CONFIG1, lines=lines), f)
+    print("config1:", len(lines) - 1, "records")
 
 
 if __name__ == "__main__":
