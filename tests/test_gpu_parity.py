@@ -92,3 +92,48 @@ def test_pair_buffer_overflow_and_no_prefilter(monkeypatch):
         e.close()
         for k in env:
             monkeypatch.delenv(k)
+
+
+def test_edge_cases(engine):
+    """Empty and degenerate inputs (the reference returns (chr, []) / no rows)."""
+    names, lens = synth.contigs(0.001, 3)
+    p = _abi.default_params(min_support=2, genotype=1)
+    engine.set_params(p)
+    engine.set_contigs(lens)
+    empty_reads = dict(chrom=np.zeros(0, np.int32), start=np.zeros(0, np.int32), end=np.zeros(0, np.int32), read_id=np.zeros(0, np.int32),
+                       is_primary=np.zeros(0, np.uint8))
+    got = engine.cluster({}, empty_reads)
+    assert len(got[0]) == 0 and len(got[2]) == 0
+    # one signature, then identical signatures from distinct reads, no reads table at all -> CSV_F_NO_READS
+    one = dict(chrom=np.array([1], np.int32), a=np.array([500], np.int32), b=np.array([60], np.int32), read_id=np.array([0], np.int32), c=None)
+    assert len(engine.cluster({"DEL": one}, empty_reads)[0]) == 0
+    same = dict(chrom=np.full(5, 1, np.int32), a=np.full(5, 500, np.int32), b=np.full(5, 60, np.int32), read_id=np.arange(5, dtype=np.int32), c=None)
+    cfg = dict(lens=lens, sigs={"DEL": same}, reads=empty_reads, params=dict(min_support=2, genotype=1))
+    _run(engine, cfg)
+    c, g, n = engine.cluster({"DEL": same}, empty_reads)
+    assert len(c) == 1 and c[0]["support"] == 5 and (c[0]["flags"] & _abi.CSV_F_NO_READS)
+    # exact duplicates collapse: five copies of one tuple are ONE signature < min_support
+    dup = dict(chrom=np.full(5, 1, np.int32), a=np.full(5, 500, np.int32), b=np.full(5, 60, np.int32), read_id=np.zeros(5, np.int32), c=None)
+    assert len(engine.cluster({"DEL": dup}, empty_reads)[0]) == 0
+
+
+def test_genome_larger_than_4gbp_uses_64bit_keys(engine):
+    """Total linear length >= 2^32 switches the radix sort to 64-bit keys (12 items per thread)."""
+    lens = np.array([2000000000, 2000000000, 1500000000], dtype=np.int64)
+    rng = np.random.default_rng(3)
+    n_reads = 4000
+    chrom = rng.integers(0, 3, n_reads).astype(np.int32)
+    start = (rng.random(n_reads) * (lens[chrom] - 30000)).astype(np.int64)
+    reads = dict(chrom=chrom, start=start.astype(np.int32), end=(start + 20000).astype(np.int32), read_id=np.arange(n_reads, dtype=np.int32),
+                 is_primary=np.ones(n_reads, np.uint8))
+    sigs = {}
+    for name in ("DEL", "INS"):
+        k = rng.integers(0, n_reads, 30000)
+        pos = start[k // 30 * 30] + 5000 + rng.integers(0, 40, 30000)   # groups of 30 reads share a locus neighbourhood
+        ln = (100 + rng.integers(0, 10, 30000)).astype(np.int32)
+        a = pos if name == "DEL" else 2 * pos
+        ok = a < 2 ** 31 - 1
+        sigs[name] = dict(chrom=chrom[k // 30 * 30][ok], a=a[ok].astype(np.int32), b=ln[ok], read_id=k[ok].astype(np.int32),
+                          c=ln[ok] if name == "INS" else None)
+    cfg = dict(lens=lens, sigs=sigs, reads=reads, params=dict(min_support=5, genotype=1))
+    assert _run(engine, cfg) > 10
