@@ -91,6 +91,13 @@ struct csv_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // uploads run on their own stream so that the H2D copy of the next SV type / the reads table
+    // overlaps the kernels of the previous type (e2e is PCIe-bound)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_up[CSV_NTYPES + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // last: reads table
+    bool up_pending[CSV_NTYPES + 1] = {false, false, false, false, false, false};
+    cudaEvent_t ev_done = nullptr;   // end of the last csv_cluster on the compute stream
+    bool done_pending = false;
     int n_sm = 148;
     csv_params P;
     bool have_params = false;
@@ -252,6 +259,12 @@ extern "C" int csv_create(int device, void* stream, csv_ctx** out) {
         if (e2 != cudaSuccess) { delete c; return set_err(CSV_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e2)); }
         c->own_stream = true;
     }
+    {
+        cudaError_t e4 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+        for (int i = 0; i <= CSV_NTYPES && e4 == cudaSuccess; i++) e4 = cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming);
+        if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
+        if (e4 != cudaSuccess) { delete c; return set_err(CSV_E_CUDA, "copy stream: %s", cudaGetErrorString(e4)); }
+    }
     csv_default_params(&c->P);
     if (const char* e = getenv("CUTESV_B200_PAIR_CAP")) c->pair_cap_override = atoll(e);
     if (const char* e = getenv("CUTESV_B200_NO_PREFILTER")) c->prefilter_enabled = atoi(e) == 0;
@@ -286,6 +299,9 @@ extern "C" int csv_destroy(csv_ctx* c) {
     extract_release(&c->ex);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int i = 0; i <= CSV_NTYPES; i++) if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return CSV_OK;
@@ -353,6 +369,21 @@ extern "C" int csv_set_profiling(csv_ctx* c, int on) {
 // ------------------------------------------------------------------------------------------
 // uploads
 // ------------------------------------------------------------------------------------------
+// The copy stream must not overwrite inputs that kernels of the previous csv_cluster still read.
+static int upload_begin(csv_ctx* c) {
+    if (c->done_pending) {
+        CU(cudaStreamWaitEvent(c->copy_stream, c->ev_done, 0));
+        c->done_pending = false;
+    }
+    return CSV_OK;
+}
+static int wait_upload(csv_ctx* c, int slot) {
+    if (c->up_pending[slot]) {
+        CU(cudaStreamWaitEvent(c->stream, c->ev_up[slot], 0));
+        c->up_pending[slot] = false;
+    }
+    return CSV_OK;
+}
 extern "C" int csv_upload_sigs(csv_ctx* c, int t, const csv_sig_cols* h) {
     if (!c || t < 0 || t >= CSV_NTYPES || !h) return set_err(CSV_E_INVALID, "bad argument");
     if (h->n < 0 || h->n >= (1ll << 30)) return set_err(CSV_E_INVALID, "signature count %lld out of range", (long long)h->n);
@@ -365,14 +396,16 @@ extern "C" int csv_upload_sigs(csv_ctx* c, int t, const csv_sig_cols* h) {
     if (!h->chrom || !h->a || !h->b || !h->read_id) return set_err(CSV_E_INVALID, "null column");
     if ((t == CSV_INS || t == CSV_INV || t == CSV_TRA) && !h->c) return set_err(CSV_E_INVALID, "column c is required for INS/INV/TRA");
     const size_t bytes = (size_t)h->n * 4;
-    stage_begin(c, CSV_ST_H2D);
+    int rc = upload_begin(c);
+    if (rc) return rc;
     CU(s.chrom.ensure(bytes)); CU(s.a.ensure(bytes)); CU(s.b.ensure(bytes)); CU(s.rid.ensure(bytes));
-    CU(cudaMemcpyAsync(s.chrom.p, h->chrom, bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(s.a.p, h->a, bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(s.b.p, h->b, bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(s.rid.p, h->read_id, bytes, cudaMemcpyHostToDevice, c->stream));
-    if (h->c) { CU(s.c.ensure(bytes)); CU(cudaMemcpyAsync(s.c.p, h->c, bytes, cudaMemcpyHostToDevice, c->stream)); }
-    stage_end(c, CSV_ST_H2D);
+    CU(cudaMemcpyAsync(s.chrom.p, h->chrom, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(s.a.p, h->a, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(s.b.p, h->b, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(s.rid.p, h->read_id, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    if (h->c) { CU(s.c.ensure(bytes)); CU(cudaMemcpyAsync(s.c.p, h->c, bytes, cudaMemcpyHostToDevice, c->copy_stream)); }
+    CU(cudaEventRecord(c->ev_up[t], c->copy_stream));
+    c->up_pending[t] = true;
     return CSV_OK;
 }
 
@@ -385,15 +418,17 @@ extern "C" int csv_upload_reads(csv_ctx* c, const csv_reads_cols* h) {
     if (h->n == 0) return CSV_OK;
     if (!h->chrom || !h->start || !h->end || !h->read_id || !h->is_primary) return set_err(CSV_E_INVALID, "null column");
     const size_t bytes = (size_t)h->n * 4;
-    stage_begin(c, CSV_ST_H2D);
+    int rc = upload_begin(c);
+    if (rc) return rc;
     CU(c->r_chrom.ensure(bytes)); CU(c->r_start.ensure(bytes)); CU(c->r_end.ensure(bytes)); CU(c->r_id.ensure(bytes));
     CU(c->r_prim.ensure((size_t)h->n));
-    CU(cudaMemcpyAsync(c->r_chrom.p, h->chrom, bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->r_start.p, h->start, bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->r_end.p, h->end, bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->r_id.p, h->read_id, bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->r_prim.p, h->is_primary, (size_t)h->n, cudaMemcpyHostToDevice, c->stream));
-    stage_end(c, CSV_ST_H2D);
+    CU(cudaMemcpyAsync(c->r_chrom.p, h->chrom, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(c->r_start.p, h->start, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(c->r_end.p, h->end, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(c->r_id.p, h->read_id, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(c->r_prim.p, h->is_primary, (size_t)h->n, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(c->ev_up[CSV_NTYPES], c->copy_stream));
+    c->up_pending[CSV_NTYPES] = true;
     return CSV_OK;
 }
 
@@ -694,6 +729,8 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
     uint32_t kslot_base = 0;
     for (int t = 0; t < CSV_NTYPES; t++) {
         if (!(type_mask >> t & 1) || c->sig[t].n == 0) continue;
+        rc = wait_upload(c, t);
+        if (rc) return rc;
         rc = (t == CSV_DEL || t == CSV_INS) ? run_indel(c, t, kslot_base) : run_other(c, t, kslot_base);
         if (rc) return rc;
         kslot_base += c->kept_cap[t];
@@ -711,6 +748,8 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
     }
     stage_end(c, CSV_ST_ORDER);
     // ---- genotype ----
+    rc = wait_upload(c, CSV_NTYPES);
+    if (rc) return rc;
     stage_begin(c, CSV_ST_GENOTYPE);
     {
         GenoJob G;
@@ -761,6 +800,8 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
     }
     stage_end(c, CSV_ST_GENOTYPE);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev_done, c->stream));
+    c->done_pending = true;
     c->ran = true;
     c->counts_valid = false;
     return CSV_OK;

@@ -15,6 +15,10 @@ extern "C" int csv_extract(csv_ctx* c, const csv_read_cols* reads, const uint32_
     CU(cudaSetDevice(c->device));
     ExtractState& X = c->ex;
     const int64_t n_sa = sa ? sa->n : 0;
+    for (int slot = 0; slot <= CSV_NTYPES; slot++) {  // extraction overwrites the device-resident inputs: drain pending uploads first
+        int wrc = wait_upload(c, slot);
+        if (wrc) return wrc;
+    }
     stage_begin(c, CSV_ST_H2D);
     int rc;
     const void* rsrc[7] = {reads->chrom, reads->ref_start, reads->ref_end, reads->flag, reads->mapq, reads->query_len, reads->read_id};
@@ -86,6 +90,8 @@ extern "C" int csv_extract(csv_ctx* c, const csv_read_cols* reads, const uint32_
         c->n_reads = h[6];
         if (n_read_rows) *n_read_rows = h[6];
         c->counts_valid = false;
+        CU(cudaEventRecord(c->ev_done, c->stream));
+        c->done_pending = true;
         if (c->profiling) stage_collect(c);
         return CSV_OK;
     }
