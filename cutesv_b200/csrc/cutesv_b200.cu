@@ -701,7 +701,7 @@ static int ensure_workspace(csv_ctx* c, uint32_t type_mask) {
     CU(c->giant_list.ensure((nm / BLOCK_M + 2) * 4));
     CU(c->giant_arena.ensure(nm * 2 * ARENA_PER_MAX + 256));
     const int ms_a = std::max(1, std::min(c->P.min_support, std::max(1, c->P.min_support_allele)));
-    c->cap_cand = (uint32_t)(n_total / ms_a + 16);
+    c->cap_cand = (uint32_t)(2 * (n_total / ms_a) + 16);  // TRA can emit two rows per chain cluster (resolveTRA.py:133-209)
     c->cap_names = (uint32_t)(n_total + 16);
     CU(c->cand_tmp.ensure((size_t)c->cap_cand * sizeof(csv_cand)));
     CU(c->cand.ensure((size_t)c->cap_cand * sizeof(csv_cand)));

@@ -87,7 +87,7 @@ class Engine(object):
             total += s.n
         r, rk = _abi.make_reads_cols(reads)
         if out is None:
-            cap_c = max(total // max(min(self.params.min_support_allele, self.params.min_support), 1) + 16, 16)
+            cap_c = max(2 * (total // max(min(self.params.min_support_allele, self.params.min_support), 1)) + 16, 16)
             cap_n = total + 16
             cands = np.zeros(cap_c, dtype=_abi.CAND_DTYPE)
             genos = np.zeros(cap_c, dtype=_abi.GENO_DTYPE)
