@@ -29,6 +29,7 @@ _SIGNATURES = {
     "csv_host_unregister": (C.c_int, [_VP]),
     "csv_upload_sigs": (C.c_int, [_VP, C.c_int, C.POINTER(_abi.csv_sig_cols)]),
     "csv_upload_reads": (C.c_int, [_VP, C.POINTER(_abi.csv_reads_cols)]),
+    "csv_upload_alignments": (C.c_int, [_VP, C.POINTER(_abi.csv_reads_cols)]),
     "csv_cluster": (C.c_int, [_VP, C.c_uint32]),
     "csv_result_counts": (C.c_int, [_VP, _I64P, _I64P]),
     "csv_fetch": (C.c_int, [_VP, _VP, _VP, C.c_int64, _I32P, C.c_int64]),

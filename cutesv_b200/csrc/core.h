@@ -58,7 +58,7 @@ struct CudaTeam {
 // status word bits written by kernels (csv_ctx reports them as CSV_E_INPUT / internal errors)
 enum : uint32_t {
     ST_BAD_CHROM = 1u, ST_BAD_POS = 2u, ST_NEG_FIELD = 4u, ST_POW_TABLE = 8u, ST_CAND_OVERFLOW = 16u,
-    ST_NAMES_OVERFLOW = 32u, ST_LIST_OVERFLOW = 64u, ST_INTERNAL = 128u
+    ST_NAMES_OVERFLOW = 32u, ST_LIST_OVERFLOW = 64u, ST_INTERNAL = 128u, ST_UNSORTED = 256u
 };
 
 // counters block in device memory (one per csv_cluster call)
@@ -880,6 +880,77 @@ CSV_HD void window_of(const csv_cand& c, int which, const GtParams& G, int64_t* 
     const int64_t x = which == 0 ? c.pos : c.pos2;
     int64_t lo = floor_half(2 * x - nb); if (2 * x - nb < 0) lo = 0;
     *s = lo; *e = ceil_half(2 * x + nb);
+}
+
+// ------------------------------------------------------------------------------------------
+// TRA genotyping from a packed all-alignments table: call_gt (resolveTRA.py:260-309) with
+// count_coverage (cuteSV_genotype.py:72-93) and threshold_ref_count (:62-70).
+// ------------------------------------------------------------------------------------------
+struct AlnView {
+    const int32_t *chrom, *start, *end, *rid;
+    const uint8_t* prim;
+    const uint32_t* off;       // first record of every contig, n_contigs + 1 entries
+    const int32_t* max_span;   // longest record per contig
+    const int64_t* contig_len;
+};
+CSV_HD int32_t threshold_ref_count(int32_t num) { return num <= 2 ? 20 * num : num <= 5 ? 9 * num : num <= 15 ? 7 * num : 5 * num; }
+CSV_HD bool sorted_contains(const int32_t* v, int n, int32_t x) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (v[mid] < x) lo = mid + 1; else hi = mid; }
+    return lo < n && v[lo] == x;
+}
+// bam.fetch(chr, s, e) in BAM order: records of the contig with start < e and end > s, by start.
+// Returns status (1, -1 or 0 = loop ran to completion); nset / dr accumulate over both regions.
+// (xs, xe): a window on the same contig whose spanning reads are ALREADY in the set (second region
+// of an intra-contig pair); xs > xe disables it.
+CSV_HD int tra_count_coverage(const AlnView& A, int32_t chr, int64_t s, int64_t e, const int32_t* sup, int n_sup, int32_t up_bound,
+                              int32_t itround, int32_t* nset, int32_t* dr, int64_t xs, int64_t xe) {
+    int64_t iteration = 0, primary = 0;
+    const uint32_t lo0 = A.off[chr], hi0 = A.off[chr + 1];
+    // first record that can still overlap: start >= s - max_span
+    uint32_t lo = lo0, hi = hi0;
+    const int64_t min_start = s - (int64_t)A.max_span[chr];
+    while (lo < hi) { uint32_t mid = lo + (hi - lo) / 2; if ((int64_t)A.start[mid] < min_start) lo = mid + 1; else hi = mid; }
+    for (uint32_t i = lo; i < hi0 && (int64_t)A.start[i] < e; i++) {
+        if (!((int64_t)A.end[i] > s)) continue;  // not returned by fetch
+        iteration++;
+        if (!A.prim[i]) continue;               // flag not in (0, 16): `continue` also skips the itround check
+        primary++;
+        if ((int64_t)A.start[i] < s && (int64_t)A.end[i] > e) {
+            const bool seen = xs <= xe && (int64_t)A.start[i] < xs && (int64_t)A.end[i] > xe;  // set.add of a known name
+            if (!seen) {
+                (*nset)++;                       // read_count.add(name): one primary record per name
+                if (!sorted_contains(sup, n_sup, A.rid[i])) (*dr)++;
+            }
+            if (*nset >= up_bound) return 1;
+        }
+        if (iteration >= itround) return ((double)primary / (double)iteration) <= 0.2 ? 1 : -1;
+    }
+    return 0;
+}
+// Fills g for one TRA candidate.  sup: its supporting read ids (ascending).
+CSV_HD void tra_call_gt(const AlnView& A, const csv_cand& c, const int32_t* sup, int32_t bias, int32_t gt_round, const csv_geno* gl_table,
+                        csv_geno* g) {
+    const int32_t chr1 = c.chrom, chr2 = c.aux >> 2;
+    const int32_t n_sup = c.names_cnt;
+    const int32_t up = threshold_ref_count(n_sup);
+    int32_t nset = 0, dr = 0;
+    int64_t s = (int64_t)c.pos - bias; if (s < 0) s = 0;
+    int64_t e = (int64_t)c.pos + bias; if (e > A.contig_len[chr1]) e = A.contig_len[chr1];
+    const int st = tra_count_coverage(A, chr1, s, e, sup, n_sup, up, gt_round, &nset, &dr, 1, 0);
+    const int64_t s1 = s, e1 = e;
+    if (st == -1) {  // DR '.', GT './.' (resolveTRA.py:277-282)
+        g->dr = -1; g->dv = n_sup; g->gt = -1; g->pl[0] = g->pl[1] = g->pl[2] = 0; g->gq = 0; g->status = 2; g->qual = 0.0;
+        return;
+    }
+    if (st == 0) {
+        s = (int64_t)c.pos2 - bias; if (s < 0) s = 0;
+        e = (int64_t)c.pos2 + bias; if (e > A.contig_len[chr2]) e = A.contig_len[chr2];
+        if (chr2 == chr1) tra_count_coverage(A, chr2, s, e, sup, n_sup, up, gt_round, &nset, &dr, s1, e1);
+        else tra_count_coverage(A, chr2, s, e, sup, n_sup, up, gt_round, &nset, &dr, 1, 0);
+    }
+    *g = gl_table[gl_index(dr, n_sup)];
+    g->dr = dr; g->dv = n_sup;
 }
 
 }  // namespace csv

@@ -111,6 +111,8 @@ struct csv_ctx {
     SigBuf sig[CSV_NTYPES];
     int64_t n_reads = 0;
     DBuf r_chrom, r_start, r_end, r_id, r_prim;
+    int64_t n_aln = 0;
+    DBuf a_chrom, a_start, a_end, a_id, a_prim, a_off, a_span;
     // sort workspace
     DBuf keys_a, keys_b, vals_a, vals_b, hist, lb_status, tickets, bkt, bkt_flags;
     bool prefilter_enabled = true;
@@ -285,7 +287,7 @@ extern "C" int csv_destroy(csv_ctx* c) {
     if (!c) return CSV_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DBuf* all[] = {&c->d_off, &c->d_len, &c->r_chrom, &c->r_start, &c->r_end, &c->r_id, &c->r_prim, &c->keys_a, &c->keys_b,
+    DBuf* all[] = {&c->a_chrom, &c->a_start, &c->a_end, &c->a_id, &c->a_prim, &c->a_off, &c->a_span, &c->d_off, &c->d_len, &c->r_chrom, &c->r_start, &c->r_end, &c->r_id, &c->r_prim, &c->keys_a, &c->keys_b,
                    &c->vals_a, &c->vals_b, &c->hist, &c->lb_status, &c->tickets, &c->bkt, &c->bkt_flags, &c->big_list, &c->giant_list, &c->giant_arena,
                    &c->cnt, &c->cand_tmp, &c->cand, &c->geno, &c->names, &c->counters, &c->bin_start, &c->bin_fill, &c->bin_bits, &c->pairs, &c->win_list,
                    &c->dr, &c->has_rows, &c->gl_table, &c->pow_half, &c->small.k_rid, &c->small.k_b, &c->small.k_prim,
@@ -429,6 +431,45 @@ extern "C" int csv_upload_reads(csv_ctx* c, const csv_reads_cols* h) {
     CU(cudaMemcpyAsync(c->r_prim.p, h->is_primary, (size_t)h->n, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_up[CSV_NTYPES], c->copy_stream));
     c->up_pending[CSV_NTYPES] = true;
+    return CSV_OK;
+}
+
+extern "C" int csv_upload_alignments(csv_ctx* c, const csv_reads_cols* h) {
+    if (!c || !h) return set_err(CSV_E_INVALID, "bad argument");
+    if (c->n_contigs == 0) return set_err(CSV_E_STATE, "csv_set_contigs has not been called");
+    if (h->n < 0 || h->n >= (1ll << 31)) return set_err(CSV_E_INVALID, "alignment count out of range");
+    CU(cudaSetDevice(c->device));
+    c->n_aln = h->n;
+    c->counts_valid = false;
+    if (h->n == 0) return CSV_OK;
+    if (!h->chrom || !h->start || !h->end || !h->read_id || !h->is_primary) return set_err(CSV_E_INVALID, "null column");
+    const size_t bytes = (size_t)h->n * 4;
+    CU(c->a_chrom.ensure(bytes)); CU(c->a_start.ensure(bytes)); CU(c->a_end.ensure(bytes)); CU(c->a_id.ensure(bytes));
+    CU(c->a_prim.ensure((size_t)h->n));
+    CU(c->a_off.ensure(((size_t)c->n_contigs + 2) * 4)); CU(c->a_span.ensure(((size_t)c->n_contigs + 2) * 4));
+    CU(c->counters.ensure(sizeof(Counters)));
+    CU(cudaMemcpyAsync(c->a_chrom.p, h->chrom, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->a_start.p, h->start, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->a_end.p, h->end, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->a_id.p, h->read_id, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->a_prim.p, h->is_primary, (size_t)h->n, cudaMemcpyHostToDevice, c->stream));
+    // contig index + sortedness check (BAM order is a precondition of the early-exit scan)
+    uint32_t* flag = nullptr;
+    CU(cudaMalloc(&flag, 4));
+    CU(cudaMemsetAsync(flag, 0, 4, c->stream));
+    CU(cudaMemsetAsync(c->a_off.p, 0xff, ((size_t)c->n_contigs + 2) * 4, c->stream));
+    CU(cudaMemsetAsync(c->a_span.p, 0, ((size_t)c->n_contigs + 2) * 4, c->stream));
+    LAUNCH(c, k_aln_index, grid_for(c, h->n, 256), 256, 0, c->a_chrom.as<int32_t>(), c->a_start.as<int32_t>(), c->a_end.as<int32_t>(), h->n,
+           c->n_contigs, c->a_off.as<uint32_t>(), c->a_span.as<int32_t>(), flag);
+    LAUNCH(c, k_aln_fill, 1, 32, 0, c->a_off.as<uint32_t>(), c->n_contigs, (uint32_t)h->n);
+    uint32_t hflag = 0;
+    CU(cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(flag);
+    if (hflag) {
+        c->n_aln = 0;
+        return set_err(CSV_E_INPUT, "alignment table: %s", (hflag & ST_UNSORTED) ? "not coordinate-sorted (BAM order required)" : "contig id out of range");
+    }
     return CSV_OK;
 }
 
@@ -797,6 +838,11 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
             }
         }
         LAUNCH(c, k_finalize, grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
+        if (c->P.genotype && c->n_aln > 0 && (type_mask >> CSV_TRA & 1) && c->sig[CSV_TRA].n > 0) {
+            AlnView A{c->a_chrom.as<int32_t>(), c->a_start.as<int32_t>(), c->a_end.as<int32_t>(), c->a_id.as<int32_t>(), c->a_prim.as<uint8_t>(),
+                      c->a_off.as<uint32_t>(), c->a_span.as<int32_t>(), c->d_len.as<int64_t>()};
+            LAUNCH(c, k_tra_genotype, grid_for(c, c->cap_cand, 128, 4), 128, 0, G, A, c->P.bias_tra, c->P.gt_round);
+        }
     }
     stage_end(c, CSV_ST_GENOTYPE);
     CU(cudaGetLastError());

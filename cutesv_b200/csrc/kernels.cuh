@@ -603,6 +603,36 @@ __global__ void k_finalize(GenoJob G) {
     }
 }
 
+// ---- TRA genotyping from the packed all-alignments table ----
+__global__ void k_aln_index(const int32_t* __restrict__ chrom, const int32_t* __restrict__ start, const int32_t* __restrict__ end, int64_t n,
+                            int32_t n_contigs, uint32_t* off, int32_t* max_span, uint32_t* status) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t c = chrom[i];
+        if (c < 0 || c >= n_contigs) { atomicOr(status, ST_BAD_CHROM); continue; }
+        if (i == 0 || chrom[i - 1] != c) off[c] = (uint32_t)i;
+        if (i > 0 && (chrom[i - 1] > c || (chrom[i - 1] == c && start[i - 1] > start[i]))) atomicOr(status, ST_UNSORTED);
+        atomicMax(&max_span[c], end[i] - start[i]);
+    }
+}
+__global__ void k_aln_fill(uint32_t* off, int32_t n_contigs, uint32_t n) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        off[n_contigs] = n;
+        for (int c = n_contigs - 1; c >= 0; c--)
+            if (off[c] == 0xffffffffu) off[c] = off[c + 1];
+    }
+}
+__global__ void k_tra_genotype(GenoJob G, AlnView A, int32_t bias, int32_t gt_round) {
+    const uint32_t n = min(G.ctr->n_cand, G.cap_cand);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const csv_cand c = G.cand[i];
+        if (c.svtype != CSV_TRA) continue;
+        csv_geno g;
+        tra_call_gt(A, c, G.names + c.names_off, bias, gt_round, G.gl_table, &g);
+        G.geno[i] = g;
+        G.cand[i].flags = c.flags & ~CSV_F_GT_HOST;
+    }
+}
+
 // cal_GL for arbitrary (c0, c1) pairs: special cases + rescale on the device, libm part from the table
 __global__ void k_cal_gl(const int32_t* c0, const int32_t* c1, int64_t n, const csv_geno* gl_table, csv_geno* out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {

@@ -56,6 +56,13 @@ class Engine(object):
         _lib.check(self.L.csv_upload_reads(self.h, C.byref(r)))
         self._keep = keep  # host buffers must outlive the async copies
 
+    def upload_alignments(self, aln):
+        """ALL alignment records in BAM order (dict like the reads table, is_primary = flag in (0, 16)): enables the
+        device TRA genotyper (call_gt, resolveTRA.py:260-309).  None / empty clears the table."""
+        r, keep = _abi.make_reads_cols(aln)
+        _lib.check(self.L.csv_upload_alignments(self.h, C.byref(r)))
+        self._keep_aln = keep
+
     def cluster_device(self, type_mask=0x1F):
         _lib.check(self.L.csv_cluster(self.h, C.c_uint32(type_mask)))
 

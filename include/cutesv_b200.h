@@ -171,6 +171,14 @@ int csv_host_unregister(void* p);
 int csv_upload_sigs(csv_ctx* ctx, int svtype, const csv_sig_cols* host_cols);
 int csv_upload_reads(csv_ctx* ctx, const csv_reads_cols* host_cols);
 
+/* Optional input of the TRA genotyper: ALL alignment records (no mapq filter, every flag) in BAM
+ * order, i.e. coordinate-sorted per contig, contigs ascending by id.  is_primary = flag in (0, 16).
+ * The reference re-opens the BAM per TRA candidate and iterates bam.fetch() with an early exit
+ * (call_gt resolveTRA.py:260-309, count_coverage cuteSV_genotype.py:72-93); with this table the same
+ * scan runs on the device.  Without it TRA rows keep CSV_F_GT_HOST.  n == 0 clears the table.
+ * Precondition (as for the reads table): one primary record per read name. */
+int csv_upload_alignments(csv_ctx* ctx, const csv_reads_cols* aln);
+
 /* Replaces process_process_sigs_type (sort + dedup, cuteSV:750-857) and the whole clustering
  * phase Pool(run_del|run_ins|run_inv|run_dup|run_tra) (cuteSV:1113-1199) including call_gt /
  * overlap_cover / assign_gt / cal_GL (cuteSV_genotype.py:33-173) for every contig at once.

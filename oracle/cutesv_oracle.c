@@ -721,6 +721,64 @@ static void resolve_tra(const Sig* v, int64_t n, const csv_params* P, Out* out) 
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* TRA genotyping: call_gt (resolveTRA.py:260-309), count_coverage / threshold_ref_count        */
+/* (cuteSV_genotype.py:62-93) over the packed all-alignments table (BAM order)                  */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { int64_t n; const int32_t *chrom, *start, *end, *rid; const uint8_t* prim; int64_t* off; } AlnTab;
+
+static int threshold_ref_count(int num) {
+    if (num <= 2) return 20 * num;
+    if (num <= 5) return 9 * num;
+    if (num <= 15) return 7 * num;
+    return 5 * num;
+}
+static int in_sorted(const int32_t* v, int n, int32_t x) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int m = (lo + hi) / 2; if (v[m] < x) lo = m + 1; else hi = m; }
+    return lo < n && v[lo] == x;
+}
+/* querydata is a set of names; with one primary record per name its size is a plain count */
+/* (xs, xe): window whose spanning reads are already in the set (same-contig second region); xs > xe: none */
+static int count_coverage(const AlnTab* A, int chr, int64_t s, int64_t e, const int32_t* sup, int n_sup, int up_bound, int itround,
+                          int* nset, int* dr, int64_t xs, int64_t xe) {
+    int64_t iteration = 0, primary = 0;
+    for (int64_t i = A->off[chr]; i < A->off[chr + 1]; i++) {
+        if (A->start[i] >= e) break;             /* f.fetch(chr, s, e): start < e and end > s, in BAM order */
+        if (!(A->end[i] > s)) continue;
+        iteration += 1;
+        if (!A->prim[i]) continue;               /* i.flag not in [0, 16] */
+        primary += 1;
+        if (A->start[i] < s && A->end[i] > e) {
+            int seen = xs <= xe && A->start[i] < xs && A->end[i] > xe; /* read_count.add() of a name already in the set */
+            if (!seen) {
+                *nset += 1;
+                if (!in_sorted(sup, n_sup, A->rid[i])) *dr += 1;
+            }
+            if (*nset >= up_bound) return 1;
+        }
+        if (iteration >= itround) return ((double)primary / (double)iteration) <= 0.2 ? 1 : -1;
+    }
+    return 0;
+}
+static void tra_genotype(const AlnTab* A, const int64_t* contig_len, const csv_params* P, csv_cand* c, const int32_t* names, csv_geno* g) {
+    int chr1 = c->chrom, chr2 = c->aux >> 2, n_sup = c->names_cnt;
+    int up = threshold_ref_count(n_sup), nset = 0, dr = 0;
+    int64_t s = (int64_t)c->pos - P->bias_tra; if (s < 0) s = 0;
+    int64_t e = (int64_t)c->pos + P->bias_tra; if (e > contig_len[chr1]) e = contig_len[chr1];
+    int st = count_coverage(A, chr1, s, e, names, n_sup, up, P->gt_round, &nset, &dr, 1, 0);
+    int64_t s1 = s, e1 = e;
+    c->flags &= ~CSV_F_GT_HOST;
+    if (st == -1) { g->dr = -1; g->dv = n_sup; g->gt = -1; g->pl[0] = g->pl[1] = g->pl[2] = 0; g->gq = 0; g->status = 2; g->qual = 0.0; return; }
+    if (st == 0) {
+        s = (int64_t)c->pos2 - P->bias_tra; if (s < 0) s = 0;
+        e = (int64_t)c->pos2 + P->bias_tra; if (e > contig_len[chr2]) e = contig_len[chr2];
+        if (chr2 == chr1) count_coverage(A, chr2, s, e, names, n_sup, up, P->gt_round, &nset, &dr, s1, e1);
+        else count_coverage(A, chr2, s, e, names, n_sup, up, P->gt_round, &nset, &dr, 1, 0);
+    }
+    csvo_cal_gl(dr, n_sup, g);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* public entry points                                                                         */
 /* ------------------------------------------------------------------------------------------ */
 
@@ -729,8 +787,7 @@ static void resolve_tra(const Sig* v, int64_t n, const csv_params* P, Out* out) 
  * Returns 0, or CSV_E_CAPACITY with the needed sizes in n_cand/n_names. */
 int csvo_cluster(const csv_params* P, int32_t n_contigs, const int64_t* contig_len, const csv_sig_cols sigs[CSV_NTYPES],
                  const csv_reads_cols* reads, uint32_t type_mask, csv_cand* cands, csv_geno* genos, int64_t cap_cand,
-                 int32_t* names, int64_t cap_names, int64_t* n_cand, int64_t* n_names, int n_threads) {
-    (void)contig_len;
+                 int32_t* names, int64_t cap_names, int64_t* n_cand, int64_t* n_names, int n_threads, const csv_reads_cols* aln) {
     ChromReads* cr = build_reads(P->genotype ? reads : NULL, n_contigs);
     Sig* sorted[CSV_NTYPES];
     int64_t ns[CSV_NTYPES];
@@ -783,6 +840,16 @@ int csvo_cluster(const csv_params* P, int32_t n_contigs, const int64_t* contig_l
             }
             if (outs[k].n_names) memcpy(names + on, outs[k].names, outs[k].n_names * sizeof(int32_t));
             on += outs[k].n_names;
+        }
+        if (P->genotype && aln && aln->n > 0) {  /* TRA rows: genotype from the all-alignments table */
+            AlnTab A;
+            A.n = aln->n; A.chrom = aln->chrom; A.start = aln->start; A.end = aln->end; A.rid = aln->read_id; A.prim = aln->is_primary;
+            A.off = (int64_t*)calloc(n_contigs + 2, sizeof(int64_t));
+            for (int64_t i = 0; i < aln->n; i++) A.off[aln->chrom[i] + 1]++;
+            for (int32_t c = 0; c < n_contigs; c++) A.off[c + 1] += A.off[c];
+            for (int64_t i = 0; i < oc; i++)
+                if (cands[i].svtype == CSV_TRA) tra_genotype(&A, contig_len, P, &cands[i], names + cands[i].names_off, &genos[i]);
+            free(A.off);
         }
     }
     for (int64_t k = 0; k < n_tasks; k++) out_free(&outs[k]);

@@ -34,6 +34,12 @@ def params_dict(p):
     return {f[0]: getattr(p, f[0]) for f in p._fields_ if f[0] != "reserved"}
 
 
+def golden_util_load(name):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import golden_util
+    return golden_util.load_case(name)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     m = ref_harness.modules()
@@ -87,6 +93,21 @@ def main():
         with open(os.path.join(OUT, name + ".json"), "w") as f:
             json.dump(dict(seed=seed, n_reads=n, params=kw, candidate={k: [list(t) for t in v] for k, v in c.items()},
                            rows=[list(t) for t in r]), f)
+    # TRA genotyping (call_gt re-opens the BAM): the reference on a fake-pysam BAM built from the reads table
+    import tempfile
+    for name in ("adv034", "adv144", "cfg3_s0p004", "adv013"):
+        case = golden_util_load(name)
+        if not case["params"].genotype:
+            continue
+        aln = ref_harness.sorted_alignments(case["reads"])
+        with tempfile.TemporaryDirectory() as d:
+            bam = os.path.join(d, "aln.bam")
+            ref_harness.write_fake_bam(bam, aln, case["names"], case["lens"], synth.read_name)
+            rows = ref_harness.run_reference(case["sigs"], case["reads"], case["names"], synth.read_name, case["params"], types_=("TRA",),
+                                             tra_bam=bam)
+        with open(os.path.join(OUT, "tragt_%s.json" % name), "w") as f:
+            json.dump({"%s|%s" % k: v for k, v in rows.items() if v}, f)
+        print("tragt", name, sum(len(v) for v in rows.values()))
     # the parity sink: VCF records the reference's generate_output + SVID loop produce from its own rows
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import golden_util

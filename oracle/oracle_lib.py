@@ -51,7 +51,7 @@ def np_std(v):
     return lib().csvo_np_std_i32(_abi.ptr(v), len(v))
 
 
-def cluster(params, lens, sigs, reads, type_mask=0x1F, n_threads=1):
+def cluster(params, lens, sigs, reads, type_mask=0x1F, n_threads=1, aln=None):
     """sigs: {type_name: cols}.  Returns (cands, genos, names) numpy arrays."""
     L = lib()
     arr = (_abi.csv_sig_cols * _abi.CSV_NTYPES)()
@@ -63,8 +63,9 @@ def cluster(params, lens, sigs, reads, type_mask=0x1F, n_threads=1):
         keep.append(k)
         total += s.n
     rc_struct, rk = _abi.make_reads_cols(reads)
+    aln_struct, ak = _abi.make_reads_cols(aln)
     lens = np.ascontiguousarray(lens, dtype=np.int64)
-    cap_c, cap_n = max(total // max(params.min_support_allele, 1), 16), max(total, 16)
+    cap_c, cap_n = max(2 * (total // max(min(params.min_support_allele, params.min_support), 1)), 16), max(total, 16)
     while True:
         cands = np.zeros(cap_c, dtype=_abi.CAND_DTYPE)
         genos = np.zeros(cap_c, dtype=_abi.GENO_DTYPE)
@@ -73,7 +74,7 @@ def cluster(params, lens, sigs, reads, type_mask=0x1F, n_threads=1):
         rc = L.csvo_cluster(C.byref(params), C.c_int32(len(lens)), lens.ctypes.data_as(C.POINTER(C.c_int64)),
                             arr, C.byref(rc_struct), C.c_uint32(type_mask),
                             cands.ctypes.data_as(C.c_void_p), genos.ctypes.data_as(C.c_void_p), C.c_int64(cap_c),
-                            _abi.ptr(names), C.c_int64(cap_n), C.byref(nc), C.byref(nn), C.c_int(n_threads))
+                            _abi.ptr(names), C.c_int64(cap_n), C.byref(nc), C.byref(nn), C.c_int(n_threads), C.byref(aln_struct))
         if rc == _abi.CSV_E_CAPACITY:
             cap_c, cap_n = max(nc.value, 16), max(nn.value, 16)
             continue

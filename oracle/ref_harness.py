@@ -25,9 +25,11 @@ def available():
 
 def _install_stubs():
     if "pysam" not in sys.modules:
-        m = types.ModuleType("pysam")
-        (m.CMATCH, m.CINS, m.CDEL, m.CREF_SKIP, m.CSOFT_CLIP, m.CHARD_CLIP, m.CPAD, m.CEQUAL, m.CDIFF,
-         m.CBACK) = range(10)
+        # the test-only fake pysam (constants + pickle-backed AlignmentFile / FastaFile)
+        fake = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "fake_pysam", "pysam.py")
+        spec = importlib.util.spec_from_file_location("pysam", fake)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
         sys.modules["pysam"] = m
     if "cigar" not in sys.modules:
         m = types.ModuleType("cigar")
@@ -141,12 +143,37 @@ def to_tuples(sigs, reads, chrom_names, read_name):
     return out
 
 
+def sorted_alignments(reads):
+    """The reads table as an all-alignments table in BAM order (contig id, start; stable)."""
+    import numpy as np
+    order = np.lexsort((np.arange(len(reads["chrom"])), reads["start"], reads["chrom"]))
+    return {k: v[order] for k, v in reads.items()}
+
+
+def write_fake_bam(path, aln, chrom_names, lens, read_name):
+    """aln: all-alignments table (BAM order) -> pickle readable by tests/fake_pysam (TRA genotyper input)."""
+    from cutesv_b200.synth import SynthRead
+    recs = []
+    for i in range(len(aln["chrom"])):
+        r = SynthRead()
+        r.reference_name = chrom_names[int(aln["chrom"][i])]
+        r.reference_start = int(aln["start"][i])
+        r.reference_end = int(aln["end"][i])
+        r.flag = 0 if int(aln["is_primary"][i]) else 2048
+        r.query_name = read_name(int(aln["read_id"][i]))
+        r.mapq, r.query_length, r.query_sequence, r.cigartuples, r.cigar, r.tags = 60, 0, "", [], [], []
+        recs.append(r)
+    with open(path, "wb") as f:
+        pickle.dump(dict(contigs=[(n, int(l)) for n, l in zip(chrom_names, lens)], reads=recs), f)
+
+
 def run_reference(sigs, reads, chrom_names, read_name, p, types_=("DEL", "INS", "INV", "DUP", "TRA"),
-                  n_pids=1):
+                  n_pids=1, tra_bam=None):
     """Reference rebuild (process_process_sigs_type, cuteSV:750-857) + clustering phase
     (cuteSV:1113-1199, run serially).  p: csv_params.  Returns {(type, chrom): rows}.
 
-    TRA is run with action=False (its call_gt needs a BAM)."""
+    TRA is run with action=False unless tra_bam (a fake-pysam BAM path) is given: its call_gt
+    re-opens the BAM."""
     m = modules()
     main = m["main"]
     tuples = to_tuples(sigs, reads, chrom_names, read_name)
@@ -191,8 +218,8 @@ def run_reference(sigs, reads, chrom_names, read_name, p, types_=("DEL", "INS", 
                 res[("DUP", c)] = rows
         if "TRA" in types_:
             for chr_ in sigs_index["TRA"]:
-                c, rows = m["tra"].run_tra((tmp, chr_, p.min_support, p.ratio_tra, p.bias_tra, "", False,
-                                            p.gt_round, sigs_index))
+                c, rows = m["tra"].run_tra((tmp, chr_, p.min_support, p.ratio_tra, p.bias_tra, tra_bam or "",
+                                            bool(tra_bam) and bool(p.genotype), p.gt_round, sigs_index))
                 res[("TRA", c)] = rows
     return res
 

@@ -138,7 +138,7 @@ void run_other(Ctx& cx, const csv_sig_cols& S, int t, uint32_t& kslot) {
 
 extern "C" int emul_cluster(const csv_params* P, int32_t n_contigs, const int64_t* contig_len, const csv_sig_cols sigs[CSV_NTYPES],
                             const csv_reads_cols* reads, uint32_t type_mask, csv_cand* cands, csv_geno* genos, int64_t cap_cand,
-                            int32_t* names, int64_t cap_names, int64_t* n_cand, int64_t* n_names) {
+                            int32_t* names, int64_t cap_names, int64_t* n_cand, int64_t* n_names, const csv_reads_cols* aln) {
     Ctx cx;
     cx.P = P; cx.n_contigs = n_contigs;
     cx.off.resize(n_contigs + 1);
@@ -222,6 +222,23 @@ extern "C" int emul_cluster(const csv_params* P, int32_t n_contigs, const int64_
             csv_geno g = cx.gl[gl_index((int32_t)dr[i], cands[i].names_cnt)];
             g.dr = (int32_t)dr[i]; g.dv = cands[i].names_cnt;
             genos[i] = g;
+        }
+    }
+    if (P->genotype && aln && aln->n > 0) {  // TRA genotyper on the packed all-alignments table (mirrors k_aln_index + k_tra_genotype)
+        std::vector<uint32_t> off(n_contigs + 2, 0xffffffffu);
+        std::vector<int32_t> span(n_contigs + 2, 0);
+        for (int64_t i = 0; i < aln->n; i++) {
+            const int32_t c = aln->chrom[i];
+            if (i == 0 || aln->chrom[i - 1] != c) off[c] = (uint32_t)i;
+            span[c] = std::max(span[c], aln->end[i] - aln->start[i]);
+        }
+        off[n_contigs] = (uint32_t)aln->n;
+        for (int c = n_contigs - 1; c >= 0; c--) if (off[c] == 0xffffffffu) off[c] = off[c + 1];
+        AlnView A{aln->chrom, aln->start, aln->end, aln->read_id, aln->is_primary, off.data(), span.data(), contig_len};
+        for (uint32_t i = 0; i < nc; i++) {
+            if (cands[i].svtype != CSV_TRA) continue;
+            tra_call_gt(A, cands[i], names + cands[i].names_off, P->bias_tra, P->gt_round, cx.gl.data(), &genos[i]);
+            cands[i].flags &= ~CSV_F_GT_HOST;
         }
     }
     return CSV_OK;

@@ -21,7 +21,7 @@ def build(force=False):
     return _SO
 
 
-def cluster(params, lens, sigs, reads, type_mask=0x1F):
+def cluster(params, lens, sigs, reads, type_mask=0x1F, aln=None):
     global _lib
     if _lib is None:
         build()
@@ -36,8 +36,9 @@ def cluster(params, lens, sigs, reads, type_mask=0x1F):
         keep.append(k)
         total += s.n
     rc_struct, rk = _abi.make_reads_cols(reads)
+    aln_struct, ak = _abi.make_reads_cols(aln)
     lens = np.ascontiguousarray(lens, dtype=np.int64)
-    cap = max(total, 16)
+    cap = max(2 * total, 16)
     cands = np.zeros(cap, dtype=_abi.CAND_DTYPE)
     genos = np.zeros(cap, dtype=_abi.GENO_DTYPE)
     names = np.zeros(cap, dtype=np.int32)
@@ -45,7 +46,7 @@ def cluster(params, lens, sigs, reads, type_mask=0x1F):
     rc = _lib.emul_cluster(C.byref(params), C.c_int32(len(lens)), lens.ctypes.data_as(C.POINTER(C.c_int64)), arr,
                            C.byref(rc_struct), C.c_uint32(type_mask), cands.ctypes.data_as(C.c_void_p),
                            genos.ctypes.data_as(C.c_void_p), C.c_int64(cap), _abi.ptr(names), C.c_int64(cap),
-                           C.byref(nc), C.byref(nn))
+                           C.byref(nc), C.byref(nn), C.byref(aln_struct))
     if rc != 0:
         raise RuntimeError("emulator failed: %d" % rc)
     return cands[:nc.value].copy(), genos[:nc.value].copy(), names[:nn.value].copy()
