@@ -2,7 +2,8 @@
 
 Same positionals, flags, defaults and pre-flight errors as the reference (cuteSV_Description.py:53-263,
 cuteSV:992-1011).  BAM decoding stays with pysam (north star); everything between decoded records and
-candidate rows runs through the C-ABI: csv_extract (replaces Pool#1), csv_cluster (Pool#2 + Pool#3).
+candidate rows runs through the C-ABI: csv_extract (replaces Pool#1), csv_cluster (Pool#2 + Pool#3,
+including the TRA genotyper, which reads a packed all-alignments table instead of re-opening the BAM).
 VCF formatting is host code (cutesv_b200/vcf.py).
 """
 import argparse
@@ -124,6 +125,7 @@ class _Accumulator(object):
         self.rows = {k: [] for k in ("chrom", "start", "end", "read_id", "is_primary")}
         self.name_id = {}
         self.names = []
+        self.aln = {k: [] for k in ("chrom", "start", "end", "read_id", "is_primary")}  # every record, BAM order
 
     def rid(self, name):
         i = self.name_id.get(name)
@@ -144,6 +146,20 @@ class _Accumulator(object):
         for k in self.rows:
             self.rows[k].append(ex["rows"][k])
 
+    def add_alignment(self, chrom_id, read):
+        a = self.aln
+        a["chrom"].append(chrom_id); a["start"].append(read.reference_start); a["end"].append(read.reference_end)
+        a["read_id"].append(self.rid(read.query_name)); a["is_primary"].append(1 if read.flag in (0, 16) else 0)
+
+    def alignments(self, rank):
+        """All-alignments table sorted by contig id (stable: BAM order inside a contig), ids as ranks."""
+        a = {k: np.asarray(v, dtype=np.uint8 if k == "is_primary" else np.int32) for k, v in self.aln.items()}
+        if len(a["chrom"]) == 0:
+            return None
+        a["read_id"] = rank[a["read_id"]]
+        order = np.argsort(a["chrom"], kind="stable")
+        return {k: v[order] for k, v in a.items()}
+
     def finish(self):
         """Concatenate and turn provisional read ids into ranks in Python string order."""
         order = sorted(range(len(self.names)), key=lambda i: self.names[i])
@@ -159,6 +175,7 @@ class _Accumulator(object):
             sigs[t] = c
         r = {k: (np.concatenate(v) if v else np.zeros(0, np.uint8 if k == "is_primary" else np.int32)) for k, v in self.rows.items()}
         r["read_id"] = rank[r["read_id"]] if len(r["read_id"]) else r["read_id"]
+        self.rank = rank
         return sigs, r, sorted_names
 
 
@@ -208,6 +225,8 @@ def main_ctrl(args, argv, engine=None):
         packet = []
         regions = None if bed is None else bed[i]
         for read in sam.fetch(task[0], task[1], task[2]):
+            if args.genotype and read.reference_start >= task[1] and read.reference_end is not None:
+                acc.add_alignment(chrom_id[task[0]], read)  # EVERY record (no filter): input of the TRA genotyper
             if read.flag == 256 or read.flag == 272:  # cuteSV:711
                 continue
             if regions is not None and not any(not (read.reference_end <= r[0] or read.reference_start >= r[1]) for r in regions):
@@ -223,22 +242,15 @@ def main_ctrl(args, argv, engine=None):
     logging.info("Rebuilding signatures of structural variants.")
     sigs, reads_cols, read_names = acc.finish()
     logging.info("Clustering structural variants.")
+    eng.upload_alignments(acc.alignments(acc.rank) if args.genotype else None)
     cands, genos, names = eng.cluster(sigs, reads_cols)
+    eng.upload_alignments(None)
     got = rows.records_to_rows(cands, genos, names, chrom_names, lambda k: read_names[k], lambda k: acc.ins_seq[k], bool(args.genotype))
-    results, tra_rows = {}, []
+    results = {}
     for t in ("DEL", "INS", "INV", "DUP", "TRA"):  # submission order of the reference, cuteSV:1116-1199
         for (tt, chrom), r in got.items():
             if tt == t:
                 results.setdefault(chrom, []).extend(r)
-                if t == "TRA":
-                    tra_rows.extend(r)
-    if args.genotype and tra_rows:  # TRA genotypes need the BAM (resolveTRA.py:260-309): completed on the host
-        from . import cuteSV_resolveTRA
-        for r in tra_rows:
-            ids = set(r[11].split(",")) if r[11] else set()
-            dv, dr, gt, gl, gq, qual = cuteSV_resolveTRA.call_gt(args.input, int(r[2]), int(r[4]), r[0], r[3], ids,
-                                                                 args.max_cluster_bias_TRA, args.gt_round)
-            r[6], r[7], r[8], r[9], r[10] = str(dr), str(gt), str(gl), str(gq), str(qual)
     logging.info("Writing to your output file.")
     reference = vcf.read_fasta(args.reference)
     opts = dict(genotype=args.genotype, max_size=args.max_size, min_size=args.min_size, report_readid=args.report_readid,
