@@ -32,6 +32,12 @@ from cutesv_b200 import _abi, synth  # noqa: E402
 
 METRIC = "sv_signatures_clustered_per_sec"
 UNIT = "signatures/s"
+WORKLOADS = {
+    2: "config2: synthetic 30x ONT WGS signature arrays, resolution_INS + resolution_DEL, --genotype",
+    3: "config3: synthetic 50x PacBio HiFi, all five SV types (INS/DEL/INV/DUP/TRA) + cal_GL genotyping (TRA from the all-alignments table)",
+    4: "config2: synthetic 30x ONT WGS signature arrays, resolution_INS + resolution_DEL, --genotype",
+    5: "config5: synthetic 100x ONT ultra-long (deep pile-ups), all five SV types + genotyping",
+}
 
 
 def parse():
@@ -137,7 +143,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "config2: synthetic 30x ONT WGS signature arrays, resolution_INS + resolution_DEL, --genotype",
+        "config": {"workload": WORKLOADS[args.config],
                    "scale": args.scale, "n_signatures_per_gpu": cfg["n_sigs"], "n_reads_per_gpu": int(len(cfg["reads"]["chrom"])),
                    "note": "CPU arm: rank 0 only, one genome-equivalent per step on all host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
@@ -200,6 +206,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if "TRA" in cfg["sigs"] and cfg["params"].get("genotype"):  # TRA genotyper input: every alignment record in BAM order
+        order = np.lexsort((np.arange(len(cfg["reads"]["chrom"])), cfg["reads"]["start"], cfg["reads"]["chrom"]))
+        eng.upload_alignments({k: v[order] for k, v in cfg["reads"].items()})
     # ---------------- device-resident: value ----------------
     eng.upload(sigs_h, reads_h)
     for _ in range(max(args.warmup, 3)):
@@ -302,7 +311,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "config2: synthetic 30x ONT WGS signature arrays, resolution_INS + resolution_DEL, --genotype",
+            "config": {"workload": WORKLOADS[args.config],
                        "scale": args.scale, "n_signatures_per_gpu": cfg["n_sigs"], "n_reads_per_gpu": int(len(cfg["reads"]["chrom"])),
                        "n_candidates": int(n_cand), "parallelism": ("contig-shard x%d (ONE genome, contigs LPT-packed over the GPUs)" if strong else
                                        "contig-shard x%d (one genome-equivalent of contigs per GPU)") % world,
