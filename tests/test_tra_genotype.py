@@ -90,3 +90,34 @@ def test_unsorted_alignment_table_is_rejected(engine):
     bad = {k: v[::-1].copy() for k, v in _aln(case["reads"]).items()}
     with pytest.raises(CuteSVError):
         engine.upload_alignments(bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_dropin_resolution_tra_with_bam(engine, tmp_path, monkeypatch, name):
+    """resolution_TRA(action=True, bam_path=...) : pysam only decodes records around the breakpoints, the
+    device genotypes.  Same rows as the reference re-opening the same (fake) BAM."""
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "tests", "fake_pysam"))
+    sys.modules.pop("pysam", None)
+    from cutesv_b200 import cuteSV_resolveTRA, runtime, workdir
+    from oracle import ref_harness
+    runtime.set_engine(engine)
+    case = golden_util.load_case(name)
+    bam = str(tmp_path / "aln.bam")
+    ref_harness.write_fake_bam(bam, _aln(case["reads"]), case["names"], case["lens"], synth.read_name)
+    s = case["sigs"]["TRA"]
+    tuples = [("ABCD"[int(s["c"][i]) & 3], int(s["a"][i]), case["names"][int(s["c"][i]) >> 2], int(s["b"][i]), synth.read_name(int(s["read_id"][i])),
+               "TRA", case["names"][int(s["chrom"][i])]) for i in range(len(s["chrom"]))]
+    path = str(tmp_path) + "/"
+    idx = workdir.write_workdir(path, {"TRA": tuples})
+    p = case["params"]
+    got = {}
+    for chrom in idx["TRA"]:
+        r = cuteSV_resolveTRA.run_tra((path, chrom, p.min_support, p.ratio_tra, p.bias_tra, bam, True, p.gt_round, idx))[1]
+        if r:
+            got[("TRA", chrom)] = r
+    d = compare.diff_rows(_golden(name), got)
+    assert not d, "\n".join(d)
+    sys.modules.pop("pysam", None)
