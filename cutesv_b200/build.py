@@ -1,4 +1,5 @@
-"""Builds libcutesv_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+"""Builds libcutesv_b200.so in-tree with nvcc for sm_100a and the host-only BAM decoder libcutesv_bam.so
+(no JIT cache: the .so files travel with the repo)."""
 import os
 import subprocess
 
@@ -11,7 +12,7 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
 
 def sources():
     d = os.path.join(HERE, "csrc")
-    out = [os.path.join(d, f) for f in sorted(os.listdir(d))]
+    out = [os.path.join(d, f) for f in sorted(os.listdir(d)) if f != "bam_reader.cpp"]  # host-only library, see bamio.py
     out.append(os.path.join(HERE, "..", "include", "cutesv_b200.h"))
     return out
 
@@ -24,6 +25,8 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    from . import bamio
+    bamio.build(force=force)   # libcutesv_bam.so (g++, zlib): the native BAM decoder
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

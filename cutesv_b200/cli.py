@@ -1,7 +1,7 @@
 """`cuteSV <bam> <ref> <vcf> <work_dir> [flags]` -- the reference's CLI shell around the B200 path.
 
 Same positionals, flags, defaults and pre-flight errors as the reference (cuteSV_Description.py:53-263,
-cuteSV:992-1011).  BAM decoding stays with pysam (north star); everything between decoded records and
+cuteSV:992-1011).  BAM decoding: the native BGZF/BAM decoder (bamio.py) for .bam input, pysam for CRAM/SAM; everything between decoded records and
 candidate rows runs through the C-ABI: csv_extract (replaces Pool#1), csv_cluster (Pool#2 + Pool#3,
 including the TRA genotyper, which reads a packed all-alignments table instead of re-opening the BAM).
 VCF formatting is host code (cutesv_b200/vcf.py).
@@ -126,6 +126,7 @@ class _Accumulator(object):
         self.name_id = {}
         self.names = []
         self.aln = {k: [] for k in ("chrom", "start", "end", "read_id", "is_primary")}  # every record, BAM order
+        self.aln_chunks = []
 
     def rid(self, name):
         i = self.name_id.get(name)
@@ -135,14 +136,15 @@ class _Accumulator(object):
             self.names.append(name)
         return i
 
-    def add(self, ex, reads, want_seq):
+    def add(self, ex, query_of, want_seq):
+        """ex: Engine.fetch_extracted(); query_of(rec) -> query sequence of record `rec` of the packet."""
         for t in _abi.TYPE_NAMES:
             for k in ("chrom", "a", "b", "read_id", "c"):
                 self.cols[t][k].append(ex["sigs"][t][k])
         s = ex["sigs"]["INS"]
         for i in range(len(s["chrom"])):
             self.ins_seq.append(packing.ins_sequence(ex["pieces"], int(ex["piece_off"][i]), int(ex["piece_cnt"][i]),
-                                                     lambda rec: reads[rec].query_sequence) if want_seq else "")
+                                                     query_of) if want_seq else "")
         for k in self.rows:
             self.rows[k].append(ex["rows"][k])
 
@@ -151,21 +153,32 @@ class _Accumulator(object):
         a["chrom"].append(chrom_id); a["start"].append(read.reference_start); a["end"].append(read.reference_end)
         a["read_id"].append(self.rid(read.query_name)); a["is_primary"].append(1 if read.flag in (0, 16) else 0)
 
+    def add_alignment_chunk(self, chrom, start, end, read_id, is_primary):
+        """Columns of many records at once (native decoder path); ids are provisional like rid()."""
+        self.aln_chunks.append(dict(chrom=chrom, start=start, end=end, read_id=read_id, is_primary=is_primary))
+
     def alignments(self, rank):
         """All-alignments table sorted by contig id (stable: BAM order inside a contig), ids as ranks."""
         a = {k: np.asarray(v, dtype=np.uint8 if k == "is_primary" else np.int32) for k, v in self.aln.items()}
+        if self.aln_chunks:
+            a = {k: np.concatenate([a[k]] + [np.asarray(c[k], dtype=a[k].dtype) for c in self.aln_chunks]) for k in a}
         if len(a["chrom"]) == 0:
             return None
         a["read_id"] = rank[a["read_id"]]
         order = np.argsort(a["chrom"], kind="stable")
         return {k: v[order] for k, v in a.items()}
 
-    def finish(self):
-        """Concatenate and turn provisional read ids into ranks in Python string order."""
-        order = sorted(range(len(self.names)), key=lambda i: self.names[i])
-        rank = np.zeros(max(len(order), 1), dtype=np.int32)
-        rank[np.array(order, dtype=np.int64)] = np.arange(len(order), dtype=np.int32)
-        sorted_names = [self.names[i] for i in order]
+    def finish(self, names=None, rank=None):
+        """Concatenate and turn provisional read ids into ranks in Python string order.  The native
+        decoder keeps the name table itself and passes (names, rank)."""
+        if names is None:
+            names = self.names
+            order = sorted(range(len(names)), key=lambda i: names[i])
+            rank = np.zeros(max(len(order), 1), dtype=np.int32)
+            rank[np.array(order, dtype=np.int64)] = np.arange(len(order), dtype=np.int32)
+        else:
+            order = np.argsort(rank[:len(names)], kind="stable")
+        sorted_names = [names[i] for i in order]
         sigs = {}
         for t in _abi.TYPE_NAMES:
             c = {k: (np.concatenate(v) if v else np.zeros(0, np.int32)) for k, v in self.cols[t].items()}
@@ -194,15 +207,11 @@ def main_ctrl(args, argv, engine=None):
         for ext in (".sigs", ".pickle"):
             if os.path.exists(tmp + t + ext):
                 raise FileExistsError("[Errno 2] File exists: '%s'" % (tmp + t + ext))
-    try:
-        import pysam
-    except ImportError:
-        raise RuntimeError("pysam is required to decode the BAM (it is the only part of the path that stays on pysam)")
     from .engine import Engine
-    sam = pysam.AlignmentFile(args.input, reference_filename=args.reference)
-    stats = sam.get_index_statistics()
+    source = _open_source(args)
+    stats = source.index_statistics()
     logging.info("The total number of chromsomes: %d" % len(stats))
-    tasks, contig_info = task_windows(stats, sam.get_reference_length, args.threads, args.batches)
+    tasks, contig_info = task_windows(stats, source.get_reference_length, args.threads, args.batches)
     bed = load_bed(args.include_bed, tasks)
     chrom_names = sorted(c[0] for c in contig_info)
     chrom_id = {n: i for i, n in enumerate(chrom_names)}
@@ -213,34 +222,9 @@ def main_ctrl(args, argv, engine=None):
     eng.set_contigs(np.array([lens[n] for n in chrom_names], dtype=np.int64))
     acc = _Accumulator()
     want_seq = not args.ignore_sequence
-
-    def flush(packet):
-        if not packet:
-            return
-        pk = packing.pack_alignments(packet, chrom_id, _NameIds(acc))
-        eng.extract(pk)
-        acc.add(eng.fetch_extracted(), packet, want_seq)
-
-    for i, task in enumerate(tasks):
-        packet = []
-        regions = None if bed is None else bed[i]
-        for read in sam.fetch(task[0], task[1], task[2]):
-            if args.genotype and read.reference_start >= task[1] and read.reference_end is not None:
-                acc.add_alignment(chrom_id[task[0]], read)  # EVERY record (no filter): input of the TRA genotyper
-            if read.flag == 256 or read.flag == 272:  # cuteSV:711
-                continue
-            if regions is not None and not any(not (read.reference_end <= r[0] or read.reference_start >= r[1]) for r in regions):
-                continue
-            if not read.reference_start >= task[1]:    # window ownership, cuteSV:725
-                continue
-            packet.append(read)
-            if len(packet) >= PACKET_READS:
-                flush(packet)
-                packet = []
-        flush(packet)
-        logging.info("Finished %s:%d-%d." % (task[0], task[1], task[2]))
+    names_rank = source.scan(args, eng, acc, tasks, bed, chrom_id, want_seq)
     logging.info("Rebuilding signatures of structural variants.")
-    sigs, reads_cols, read_names = acc.finish()
+    sigs, reads_cols, read_names = acc.finish(*names_rank)
     logging.info("Clustering structural variants.")
     eng.upload_alignments(acc.alignments(acc.rank) if args.genotype else None)
     cands, genos, names = eng.cluster(sigs, reads_cols)
@@ -258,8 +242,125 @@ def main_ctrl(args, argv, engine=None):
     vcf.write_vcf(args.output, results, reference, contig_info, args.sample, argv, opts)
     if args.retain_work_dir:
         _write_workdir(tmp, sigs, reads_cols, chrom_names, read_names, acc.ins_seq, args.write_old_sigs)
-    sam.close()
+    source.close()
     return results
+
+
+def _open_source(args):
+    """BAM decoding backend: the native decoder (csrc/bam_reader.cpp) for BGZF BAM input, pysam for
+    everything else (CRAM, SAM).  CUTESV_B200_BAM=native|pysam forces one."""
+    from . import bamio
+    want = os.environ.get("CUTESV_B200_BAM", "auto")
+    if want == "native" or (want == "auto" and bamio.is_bam(args.input)):
+        return _NativeSource(args)
+    try:
+        import pysam
+    except ImportError:
+        raise RuntimeError("pysam is required to decode this input (only BGZF-compressed BAM is decoded natively)")
+    return _PysamSource(pysam.AlignmentFile(args.input, reference_filename=args.reference))
+
+
+class _PysamSource(object):
+    """Window-by-window pysam iteration, the reference's own access pattern (cuteSV:697-733)."""
+
+    def __init__(self, sam):
+        self.sam = sam
+
+    def index_statistics(self):
+        return self.sam.get_index_statistics()
+
+    def get_reference_length(self, name):
+        return self.sam.get_reference_length(name)
+
+    def close(self):
+        self.sam.close()
+
+    def scan(self, args, eng, acc, tasks, bed, chrom_id, want_seq):
+        def flush(packet):
+            if not packet:
+                return
+            pk = packing.pack_alignments(packet, chrom_id, _NameIds(acc))
+            eng.extract(pk)
+            acc.add(eng.fetch_extracted(), lambda rec: packet[rec].query_sequence, want_seq)
+
+        for i, task in enumerate(tasks):
+            packet = []
+            regions = None if bed is None else bed[i]
+            for read in self.sam.fetch(task[0], task[1], task[2]):
+                if args.genotype and read.reference_start >= task[1] and read.reference_end is not None:
+                    acc.add_alignment(chrom_id[task[0]], read)  # EVERY record (no filter): input of the TRA genotyper
+                if read.flag == 256 or read.flag == 272:  # cuteSV:711
+                    continue
+                if regions is not None and not any(not (read.reference_end <= r[0] or read.reference_start >= r[1]) for r in regions):
+                    continue
+                if not read.reference_start >= task[1]:    # window ownership, cuteSV:725
+                    continue
+                packet.append(read)
+                if len(packet) >= PACKET_READS:
+                    flush(packet)
+                    packet = []
+            flush(packet)
+            logging.info("Finished %s:%d-%d." % (task[0], task[1], task[2]))
+        return None, None
+
+
+class _NativeSource(object):
+    """One sequential pass over the BAM with the native decoder: every mapped record is seen once, in
+    file order -- the same sequence the window loop above yields for a coordinate-sorted BAM, since a
+    record is owned by the window its start falls in (cuteSV:725)."""
+
+    def __init__(self, args):
+        from . import bamio
+        self.bamio = bamio
+        self.rd = bamio.BamReader(args.input, threads=max(1, min(int(args.threads), 32)), keep_seq=not args.ignore_sequence)
+
+    def index_statistics(self):
+        return self.rd.index_statistics()
+
+    def get_reference_length(self, name):
+        return self.rd.get_reference_length(name)
+
+    def close(self):
+        self.rd.close()
+
+    def scan(self, args, eng, acc, tasks, bed, chrom_id, want_seq):
+        bamio, rd = self.bamio, self.rd
+        rd.set_chrom_ids(chrom_id)
+        # window starts per contig id -> owning task of a record (only the bed filter needs it)
+        starts, first_task = {}, {}
+        for i, t in enumerate(tasks):
+            starts.setdefault(chrom_id[t[0]], []).append(t[1])
+            first_task.setdefault(chrom_id[t[0]], i)
+        n_seen = 0
+        while True:
+            pk = rd.next_packet(PACKET_READS)
+            if pk is None:
+                break
+            has_cigar = pk["cigar_off"][1:] > pk["cigar_off"][:-1]   # reference_end is None otherwise
+            if args.genotype:
+                v = np.flatnonzero(has_cigar)
+                acc.add_alignment_chunk(pk["chrom"][v], pk["ref_start"][v], pk["ref_end"][v], pk["read_id"][v],
+                                        ((pk["flag"][v] == 0) | (pk["flag"][v] == 16)).astype(np.uint8))
+            keep = has_cigar & (pk["flag"] != 256) & (pk["flag"] != 272) & (pk["chrom"] >= 0)
+            if bed is not None:
+                owner = np.zeros(len(keep), dtype=np.int64)
+                for c in np.unique(pk["chrom"]):
+                    m = pk["chrom"] == c
+                    if int(c) in starts:
+                        owner[m] = first_task[int(c)] + np.searchsorted(np.asarray(starts[int(c)], dtype=np.float64), pk["ref_start"][m], side="right") - 1
+                for ti in np.unique(owner[keep]):
+                    m = keep & (owner == ti)
+                    hit = np.zeros(len(keep), dtype=bool)
+                    for r in bed[int(ti)]:
+                        hit |= ~((pk["ref_end"] <= r[0]) | (pk["ref_start"] >= r[1]))
+                    keep[m & ~hit] = False
+            sub = bamio.subset_packet(pk, np.flatnonzero(keep))
+            if len(sub["chrom"]):
+                eng.extract(sub)
+                acc.add(eng.fetch_extracted(), lambda rec: bamio.decode_seq(sub, rec), want_seq)
+            n_seen += len(keep)
+            logging.info("Decoded %d records." % n_seen)
+        return rd.names(), rd.name_ranks()
 
 
 class _NameIds(object):

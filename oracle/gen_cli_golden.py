@@ -29,6 +29,17 @@ def materialise(d, seed=1):
     return bam, fa, os.path.join(d, "out.vcf"), wd
 
 
+BED_ROWS = [("chrA", 20000, 50000), ("chrA", 70000, 71000), ("chrA", 100500, 104000), ("chrB", 10000, 60000), ("chrB", 88000, 90500)]
+
+
+def write_bed(d):
+    """-include_bed input of the third golden (regions straddle task-window borders)."""
+    bed = os.path.join(d, "inc.bed")
+    with open(bed, "w") as f:
+        f.write("".join("%s\t%d\t%d\n" % r for r in BED_ROWS))
+    return bed
+
+
 # BASELINE.json configs[0]: BED-driven chr22 INS+DEL, ~5k reads, reference CPU path --threads 4, ONT preset
 FLAGS_CONFIG1 = ["--genotype", "-s", "5", "--threads", "4", "--max_cluster_bias_INS", "100", "--diff_ratio_merging_INS", "0.3",
                  "--max_cluster_bias_DEL", "100", "--diff_ratio_merging_DEL", "0.3"]
@@ -69,6 +80,14 @@ def main():
     with open(os.path.join(ROOT, "tests", "golden", "cli_config1.json"), "w") as f:
         json.dump(dict(flags=FLAGS_CONFIG1, lines=lines), f)
     print("config1:", len(lines) - 1, "records")
+    d2 = tempfile.mkdtemp()
+    bam, fa, out, wd = materialise(d2)
+    argv = [bam, fa, out, wd] + FLAGS + ["-include_bed", write_bed(d2)]
+    m["main"].main_ctrl(parseArgs(argv), argv)
+    lines = [l for l in open(out) if not l.startswith("##")]
+    with open(os.path.join(ROOT, "tests", "golden", "cli_dataset1_bed.json"), "w") as f:
+        json.dump(dict(flags=FLAGS, lines=lines), f)
+    print("dataset1 + include_bed:", len(lines) - 1, "records")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,109 @@
+"""Native BAM decoder (cutesv_b200/bamio.py) against the per-read Python packer on the same records."""
+import os
+
+import numpy as np
+import pytest
+
+import bam_writer
+from cutesv_b200 import bamio, packing, synth
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    bamio.build()
+
+
+def _sorted_reads(seed, n_reads, with_seq=True):
+    reads, names, lens = synth.synth_alignments(seed, n_reads=n_reads, with_seq=with_seq)
+    contigs = list(zip(names, (int(x) for x in lens)))
+    order = {n: i for i, n in enumerate(names)}
+    reads.sort(key=lambda r: (order[r.reference_name], r.reference_start))
+    return reads, contigs
+
+
+def _read_all(path, chrom_id, chunk, **kw):
+    rd = bamio.BamReader(path, **kw)
+    rd.set_chrom_ids(chrom_id)
+    packets = []
+    while True:
+        pk = rd.next_packet(chunk)
+        if pk is None:
+            break
+        packets.append(pk)
+    return rd, packets
+
+
+@pytest.mark.parametrize("seed,chunk,via_cg", [(1, 1000, False), (2, 37, False), (3, 64, True)])
+def test_packet_equals_python_packer(tmp_path, seed, chunk, via_cg):
+    reads, contigs = _sorted_reads(seed, 300)
+    path = str(tmp_path / "a.bam")
+    bam_writer.write_bam(path, contigs, reads, long_cigar_via_cg=via_cg, block_bytes=9000, extra_unmapped=3)
+    chrom_names = sorted(n for n, _ in contigs)
+    chrom_id = {n: i for i, n in enumerate(chrom_names)}
+    rd, packets = _read_all(path, chrom_id, chunk, threads=3)
+    assert rd.references == [n for n, _ in contigs] and rd.lengths == [l for _, l in contigs]
+    names = rd.names()
+    o = 0
+    for pk in packets:
+        n = len(pk["chrom"])
+        assert n <= chunk
+        sub = reads[o:o + n]
+        want = packing.pack_alignments(sub, chrom_id, {nm: i for i, nm in enumerate(names)})
+        for k in ("chrom", "ref_start", "ref_end", "flag", "mapq", "query_len", "read_id", "cigar_off", "sa_off", "cigar"):
+            assert np.array_equal(pk[k], want[k]), k
+        for k in want["sa"]:
+            assert np.array_equal(pk["sa"][k], want["sa"][k]), k
+        for i in (0, n // 2, n - 1):
+            assert bamio.decode_seq(pk, i) == sub[i].query_sequence
+        o += n
+    assert o == len(reads)  # the unplaced records at the end are not returned
+    rank, uniq = packing.name_ranks(names)
+    assert np.array_equal(rd.name_ranks()[:len(names)], rank) and sorted(names) == uniq
+    assert rd.index_statistics() == [(nm, sum(1 for r in reads if r.reference_name == nm)) for nm, _ in contigs]
+    rd.close()
+
+
+def test_subset_packet(tmp_path):
+    reads, contigs = _sorted_reads(5, 120)
+    path = str(tmp_path / "b.bam")
+    bam_writer.write_bam(path, contigs, reads)
+    chrom_id = {n: i for i, n in enumerate(sorted(n for n, _ in contigs))}
+    rd, packets = _read_all(path, chrom_id, 1000)
+    pk = packets[0]
+    keep = np.flatnonzero((pk["flag"] != 256) & (pk["flag"] != 272))
+    sub = bamio.subset_packet(pk, keep)
+    names = rd.names()
+    want = packing.pack_alignments([reads[i] for i in keep], chrom_id, {nm: i for i, nm in enumerate(names)})
+    for k in ("chrom", "ref_start", "ref_end", "flag", "mapq", "query_len", "read_id", "cigar_off", "sa_off", "cigar"):
+        assert np.array_equal(sub[k], want[k]), k
+    for k in want["sa"]:
+        assert np.array_equal(sub["sa"][k], want["sa"][k]), k
+    for j in (0, len(keep) - 1):
+        assert bamio.decode_seq(sub, j) == reads[keep[j]].query_sequence
+    rd.close()
+
+
+def test_errors(tmp_path):
+    bad = tmp_path / "bad.bam"
+    bad.write_bytes(b"this is not a bam file at all, just text")
+    assert not bamio.is_bam(str(bad))
+    with pytest.raises(IOError):
+        bamio.BamReader(str(bad))
+    with pytest.raises(IOError):
+        bamio.BamReader(str(tmp_path / "missing.bam"))
+    reads, contigs = _sorted_reads(7, 50)
+    path = str(tmp_path / "t.bam")
+    bam_writer.write_bam(path, contigs, reads)
+    assert bamio.is_bam(path)
+    data = open(path, "rb").read()
+    trunc = tmp_path / "trunc.bam"
+    trunc.write_bytes(data[:len(data) // 2])
+    with pytest.raises(IOError, match="truncated"):
+        rd = bamio.BamReader(str(trunc))
+        while rd.next_packet(1000) is not None:
+            pass
+    os.remove(path + ".bai")
+    rd = bamio.BamReader(path)
+    with pytest.raises(IOError):
+        rd.index_statistics()
+    rd.close()

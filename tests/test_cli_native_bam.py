@@ -1,0 +1,81 @@
+"""The CLI shell on a REAL .bam (written by tests/bam_writer.py) through the native decoder:
+VCF body identical to what the reference's own main_ctrl wrote for the same records
+(tests/golden/cli_dataset1.json / cli_config1.json, made by oracle/gen_cli_golden.py).
+CPU variant: kernels replaced by the pipeline emulator; -m gpu variant: the CUDA path."""
+import json
+import os
+import pickle
+
+import pytest
+
+import bam_writer
+import golden_util
+from cutesv_b200 import bamio, cli
+from oracle import gen_cli_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _to_real_bam(pickled, path):
+    ds = pickle.load(open(pickled, "rb"))
+    order = {n: i for i, (n, _) in enumerate(ds["contigs"])}
+    reads = sorted(ds["reads"], key=lambda r: (order[r.reference_name], r.reference_start))  # stable, like an indexed BAM
+    bam_writer.write_bam(path, ds["contigs"], reads, extra_unmapped=2)
+    return path
+
+
+def _run(engine, tmp_path, which, extra=()):
+    bamio.build()
+    if which in (1, 3):
+        gold = json.load(open(os.path.join(golden_util.GOLDEN, "cli_dataset1.json" if which == 1 else "cli_dataset1_bed.json")))
+        pk, fa, out, wd = gen_cli_golden.materialise(str(tmp_path))
+        if which == 3:   # -include_bed: the read filter of cuteSV:717-723 with window-assigned regions
+            extra = list(extra) + ["-include_bed", gen_cli_golden.write_bed(str(tmp_path))]
+    else:
+        gold = json.load(open(os.path.join(golden_util.GOLDEN, "cli_config1.json")))
+        pk, fa, out, wd = gen_cli_golden.materialise_config1(str(tmp_path))
+    bam = _to_real_bam(pk, str(tmp_path / "real.bam"))
+    assert bamio.is_bam(bam)
+    argv = [bam, fa, out, wd] + gold["flags"] + list(extra)
+    cli.main_ctrl(cli.build_parser().parse_args(argv), argv, engine=engine)
+    return [l for l in open(out) if not l.startswith("##")], gold["lines"], wd
+
+
+def test_cli_native_bam_dataset1_cpu(tmp_path):
+    from emul_engine import EmulEngine
+    lines, gold, wd = _run(EmulEngine(), tmp_path, 1, ["--retain_work_dir"])
+    assert lines == gold
+    assert os.path.exists(os.path.join(wd, "reads.pickle"))
+
+
+def test_cli_native_bam_config1_cpu(tmp_path):
+    from emul_engine import EmulEngine
+    lines, gold, _ = _run(EmulEngine(), tmp_path, 2)
+    assert len(lines) > 250 and lines == gold
+
+
+def test_cli_native_bam_include_bed_cpu(tmp_path):
+    from emul_engine import EmulEngine
+    lines, gold, _ = _run(EmulEngine(), tmp_path, 3)
+    assert 5 < len(lines) < 28 and lines == gold
+
+
+def test_cli_pysam_path_include_bed_cpu(tmp_path, monkeypatch):
+    """Same golden through the pysam-shaped source (window-by-window fetch) with the test-only fake pysam."""
+    import sys
+    from emul_engine import EmulEngine
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "tests", "fake_pysam"))
+    sys.modules.pop("pysam", None)
+    gold = json.load(open(os.path.join(golden_util.GOLDEN, "cli_dataset1_bed.json")))
+    bam, fa, out, wd = gen_cli_golden.materialise(str(tmp_path))
+    argv = [bam, fa, out, wd] + gold["flags"] + ["-include_bed", gen_cli_golden.write_bed(str(tmp_path))]
+    cli.main_ctrl(cli.build_parser().parse_args(argv), argv, engine=EmulEngine())
+    assert [l for l in open(out) if not l.startswith("##")] == gold["lines"]
+    sys.modules.pop("pysam", None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", [1, 2, 3])
+def test_cli_native_bam_gpu(engine, tmp_path, which):
+    lines, gold, _ = _run(engine, tmp_path, which)
+    assert lines == gold
