@@ -180,12 +180,122 @@ CSV_HD uint32_t team_excl_scan(Team tm, uint32_t* arr, int n, int64_t* red) {
     return total;
 }
 
-struct K128 { uint64_t hi, lo; };
+// in-place exclusive scan of a 0/1 flag array; returns the number of set flags
+template <class Team>
+CSV_HD uint32_t team_flag_scan(Team tm, uint32_t* arr, int n, int64_t* red) {
+#if defined(__CUDA_ARCH__)
+    if (Team::SIZE == 32) {  // warp team: one ballot per 32 flags
+        const int lane = tm.tid();
+        uint32_t run = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const bool f = i < n && arr[i] != 0;
+            const uint32_t mask = __ballot_sync(0xffffffffu, f);
+            if (i < n) arr[i] = run + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+            run += (uint32_t)__popc(mask);
+        }
+        __syncwarp();
+        return run;
+    }
+#endif
+    return team_excl_scan(tm, arr, n, red);
+}
+
+struct alignas(16) K128 { uint64_t hi, lo; };
 CSV_HD bool k128_gt(const K128& a, const K128& b) { return a.hi > b.hi || (a.hi == b.hi && a.lo > b.lo); }
+
+#if defined(__CUDA_ARCH__)
+// Warp-team bitonic sort held in registers: element i = e*32 + lane lives in register slot e of its
+// lane.  Exchange distances < 32 are butterfly shuffles (every lane busy, no shared-memory round
+// trips); distances >= 32 are register-to-register inside the lane with a direction known at compile
+// time.  KW = key width in 64-bit words (1: `hi` only), HASV = carry a 32-bit payload.  All keys in
+// this file are unique (an index is part of every key), so any correct sort gives the same result
+// as the shared-memory version below.
+template <int E, int KW, bool HASV>
+__device__ __noinline__ void warp_sort_regs(uint64_t* a, uint32_t* v, int M) {
+    const int lane = (int)(threadIdx.x & 31);
+    uint64_t hi[E], lo[E];
+    uint32_t pv[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int i = e * 32 + lane;
+        if (i < M) {
+            if (KW == 2) { const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(a + 2 * i); hi[e] = x.x; lo[e] = x.y; }
+            else { hi[e] = a[i]; lo[e] = 0; }
+            pv[e] = HASV ? v[i] : 0u;
+        } else { hi[e] = ~0ull; lo[e] = ~0ull; pv[e] = 0u; }
+    }
+    // one butterfly stage at distance j < 32 inside blocks of size k (rolled: the code stays small enough
+    // for the instruction cache; j and k are warp-uniform run-time values)
+    auto shuffle_stage = [&](int k, int j) {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const bool up = (((e * 32 + lane) & k) == 0);
+            const uint64_t ohi = __shfl_xor_sync(0xffffffffu, hi[e], j);
+            const uint64_t olo = KW == 2 ? __shfl_xor_sync(0xffffffffu, lo[e], j) : 0ull;
+            const uint32_t opv = HASV ? __shfl_xor_sync(0xffffffffu, pv[e], j) : 0u;
+            const bool gt = hi[e] > ohi || (KW == 2 && hi[e] == ohi && lo[e] > olo);
+            const bool lt = hi[e] < ohi || (KW == 2 && hi[e] == ohi && lo[e] < olo);
+            // the lower index keeps the minimum in an ascending region, the maximum otherwise
+            const bool take = (lower == up) ? gt : lt;
+            if (take) { hi[e] = ohi; if (KW == 2) lo[e] = olo; if (HASV) pv[e] = opv; }
+        }
+    };
+    const int kmax = M < 32 ? M : 32;   // M < 32: the padding lanes already hold all-ones and never move
+#pragma unroll 1
+    for (int k = 2; k <= kmax; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j > 0; j >>= 1) shuffle_stage(k, j);
+    }
+#pragma unroll
+    for (int k = 64; k <= 32 * E; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j >= 32; j >>= 1) {   // register-to-register inside the lane, direction known statically
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                const int pe = e ^ (j >> 5);
+                if (pe > e) {
+                    const bool up = ((e * 32) & k) == 0;
+                    const bool gt = hi[e] > hi[pe] || (KW == 2 && hi[e] == hi[pe] && lo[e] > lo[pe]);
+                    if (gt == up) {
+                        uint64_t t0 = hi[e]; hi[e] = hi[pe]; hi[pe] = t0;
+                        if (KW == 2) { uint64_t t1 = lo[e]; lo[e] = lo[pe]; lo[pe] = t1; }
+                        if (HASV) { uint32_t t2 = pv[e]; pv[e] = pv[pe]; pv[pe] = t2; }
+                    }
+                }
+            }
+        }
+#pragma unroll 1
+        for (int j = 16; j > 0; j >>= 1) shuffle_stage(k, j);
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int i = e * 32 + lane;
+        if (i < M) {
+            if (KW == 2) *reinterpret_cast<ulonglong2*>(a + 2 * i) = make_ulonglong2(hi[e], lo[e]);
+            else a[i] = hi[e];
+            if (HASV) v[i] = pv[e];
+        }
+    }
+    __syncwarp();
+}
+template <int KW, bool HASV>
+__device__ __forceinline__ void warp_sort_dispatch(uint64_t* a, uint32_t* v, int M) {
+    if (M <= 32) warp_sort_regs<1, KW, HASV>(a, v, M);
+    else if (M <= 64) warp_sort_regs<2, KW, HASV>(a, v, M);
+    else warp_sort_regs<4, KW, HASV>(a, v, M);
+}
+#define CSV_WARP_SORT(KW, HASV, a, v, M) \
+    if (Team::SIZE == 32 && (M) <= 128) { warp_sort_dispatch<KW, HASV>((uint64_t*)(a), (v), (M)); return; }
+#else
+#define CSV_WARP_SORT(KW, HASV, a, v, M)
+#endif
 
 // bitonic sorts, ascending, M a power of two (callers pad with all-ones keys)
 template <class Team>
 CSV_HD void team_sort_k128(Team tm, K128* a, int M) {
+    CSV_WARP_SORT(2, false, a, (uint32_t*)nullptr, M)
     for (int k = 2; k <= M; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tm.tid(); i < M; i += Team::SIZE) {
@@ -201,6 +311,7 @@ CSV_HD void team_sort_k128(Team tm, K128* a, int M) {
 }
 template <class Team>
 CSV_HD void team_sort_k128_kv(Team tm, K128* a, uint32_t* v, int M) {
+    CSV_WARP_SORT(2, true, a, v, M)
     for (int k = 2; k <= M; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tm.tid(); i < M; i += Team::SIZE) {
@@ -219,6 +330,7 @@ CSV_HD void team_sort_k128_kv(Team tm, K128* a, uint32_t* v, int M) {
 }
 template <class Team>
 CSV_HD void team_sort_u64(Team tm, uint64_t* a, int M) {
+    CSV_WARP_SORT(1, false, a, (uint32_t*)nullptr, M)
     for (int k = 2; k <= M; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tm.tid(); i < M; i += Team::SIZE) {
@@ -234,6 +346,7 @@ CSV_HD void team_sort_u64(Team tm, uint64_t* a, int M) {
 }
 template <class Team>
 CSV_HD void team_sort_kv(Team tm, uint64_t* a, uint32_t* v, int M) {
+    CSV_WARP_SORT(1, true, a, v, M)
     for (int k = 2; k <= M; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tm.tid(); i < M; i += Team::SIZE) {
@@ -319,6 +432,36 @@ CSV_HD double np_std(G get_int, int64_t n, int64_t sum) {
 // cal_CIPOS (cuteSV_genotype.py:58-60) with the libm-pow table
 CSV_HD int32_t cal_cipos(double std, int64_t n, const double* pow_half) { return (int32_t)(1.96 * std / pow_half[n]); }
 
+#if defined(__CUDA_ARCH__)
+// np.std of n <= 128 values for TWO arrays at once on a warp: lanes 0-7 own numpy's eight strided
+// accumulators r0..r7 of array 0, lanes 8-15 those of array 1 (np_pairwise_leaf above, same additions
+// in the same order: the r_j chains are independent, the tree (r0+r1)+(r2+r3)... is a xor-butterfly
+// of commutative adds, the tail is added sequentially).  Returns the std in lanes 0-7 / 8-15.
+template <class G0, class G1>
+__device__ __forceinline__ double warp_np_std2(G0 get0, G1 get1, int n, int64_t sum0, int64_t sum1) {
+    const int lane = (int)(threadIdx.x & 31);
+    const int which = (lane >> 3) & 1, j = lane & 7;
+    const double mean = (double)(which ? sum1 : sum0) / (double)n;
+    auto sq = [&](int i) { const double x = (double)(which ? get1(i) : get0(i)) - mean; return x * x; };
+    double res;
+    if (n < 8) {
+        res = 0.;
+        for (int i = 0; i < n; i++) res += sq(i);
+    } else {
+        const int n8 = n - (n % 8);
+        double r = sq(j);
+        for (int i = 8 + j; i < n8; i += 8) r += sq(i);
+        r = r + __shfl_xor_sync(0xffffffffu, r, 1);
+        r = r + __shfl_xor_sync(0xffffffffu, r, 2);
+        r = r + __shfl_xor_sync(0xffffffffu, r, 4);
+        res = r;
+        for (int i = n8; i < n; i++) res += sq(i);
+    }
+    res = res / (double)n;
+    return sqrt(res);
+}
+#endif
+
 // rescale_read_counts (cuteSV_genotype.py:25-31) + index into the host-built cal_GL table
 // (table[c0*101+c1] for c0+c1 <= 100; slots 10201 / 10202 hold the (3,1) and (6,2) specials).
 CSV_HD int32_t gl_index(int32_t c0, int32_t c1) {
@@ -377,14 +520,21 @@ struct IndelArena {
     }
 };
 
-CSV_HD bool emit_reserve(const Emit& E, uint32_t n_names, uint32_t* slot, uint32_t* noff) {
-    // called by one thread
-    uint32_t s = atomic_add_u32(&E.ctr->n_cand, 1u);
-    uint32_t o = atomic_add_u32(&E.ctr->n_names, n_names);
-    *slot = s; *noff = o;
+// two halves so that a caller can issue the two returning atomics early and look at their results
+// only after other work (their round trip to L2 is ~1 us)
+CSV_HD void emit_reserve_issue(const Emit& E, uint32_t n_names, uint32_t* slot, uint32_t* noff) {
+    *slot = atomic_add_u32(&E.ctr->n_cand, 1u);
+    *noff = atomic_add_u32(&E.ctr->n_names, n_names);
+}
+CSV_HD bool emit_reserve_check(const Emit& E, uint32_t n_names, uint32_t s, uint32_t o) {
     if (s >= E.lim.cap_cand) { atomic_or_u32(&E.ctr->status, ST_CAND_OVERFLOW); return false; }
     if ((uint64_t)o + n_names > E.lim.cap_names) { atomic_or_u32(&E.ctr->status, ST_NAMES_OVERFLOW); return false; }
     return true;
+}
+CSV_HD bool emit_reserve(const Emit& E, uint32_t n_names, uint32_t* slot, uint32_t* noff) {
+    // called by one thread
+    emit_reserve_issue(E, n_names, slot, noff);
+    return emit_reserve_check(E, n_names, *slot, *noff);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -434,7 +584,7 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
     };
     for (int q = t; q < m; q += Team::SIZE) A.F[q] = keep_fn(q) ? 1u : 0u;
     tm.sync();
-    const int m2 = (int)team_excl_scan(tm, A.F, m, red);
+    const int m2 = (int)team_flag_scan(tm, A.F, m, red);
     int32_t* D_pos = A.D; int32_t* D_len = A.D + M; int32_t* D_rid = A.D + 2 * M; int32_t* D_aux = A.D + 3 * M;
     int32_t* D_idx = A.D + 4 * M;
     for (int q = t; q < m; q += Team::SIZE) {
@@ -455,7 +605,7 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
     //    (strictly larger replaces), kept at the dict position of the read's first occurrence
     for (int q = t; q < m2; q += Team::SIZE) A.F[q] = (q == 0 || D_rid[q] != D_rid[q - 1]) ? 1u : 0u;
     tm.sync();
-    const int u = (int)team_excl_scan(tm, A.F, m2, red);
+    const int u = (int)team_flag_scan(tm, A.F, m2, red);
     if (u < P.min_support) {  // len(read_tag) < read_count (:133)
         if (t == 0) E.cnt[kslot] = 0;
         return;
@@ -494,7 +644,7 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
     };
     for (int i = t; i < u; i += Team::SIZE) A.F[i] = brk(i) ? 1u : 0u;
     tm.sync();
-    const int na = (int)team_excl_scan(tm, A.F, u, red) + 1;
+    const int na = (int)team_flag_scan(tm, A.F, u, red) + 1;
     for (int i = t; i < u; i += Team::SIZE)
         if (i == 0 || brk(i)) A.VA[A.F[i] + (brk(i) ? 1u : 0u)] = (uint32_t)i;
     tm.sync();
@@ -506,7 +656,7 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
         } else A.KA[a] = ~0ull;
     }
     tm.sync();
-    team_sort_kv(tm, A.KA, A.VA, MA);
+    if (na > 1) team_sort_kv(tm, A.KA, A.VA, MA);
     // 5. one candidate per allele with enough support (:165-219 / 370-432)
     uint32_t n_emit = 0;
     for (int k = 0; k < na; k++) {
@@ -537,6 +687,26 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
             const int64_t imin = team_min(tm, bi, red);
             search = D_pos[V3[st + imin]];  // search_threshold = allele_list[0] (:177)
         }
+        // INS: first member (allele order) whose sequence is long enough (:399-405).  It needs signalLen, which
+        // with remain == n (the default remain_reads_ratio) is known here, otherwise only after the remain sort.
+        int32_t pos_pick = 0, aux = 0;
+        uint32_t slot = 0, noff = 0;
+        bool reserved = false;
+        if (svtype != CSV_INS || remain >= n) {
+            bool drop = false;
+            if (svtype == CSV_INS) {
+                const int32_t need = (int32_t)((double)sl / (double)remain);
+                int64_t bi = INT64_MAX;
+                for (int i = t; i < n; i += Team::SIZE)
+                    if (D_aux[V3[st + i]] >= need && i < bi) bi = i;
+                const int64_t pick = team_min(tm, bi, red);
+                if (pick == INT64_MAX) drop = true;  // ideal_ins_seq == '<INS>' -> dropped
+                else { pos_pick = D_pos[V3[st + pick]]; aux = D_idx[V3[st + pick]]; }
+            }
+            if (drop) continue;
+            if (t == 0) emit_reserve_issue(E, (uint32_t)n, &slot, &noff);   // results are looked at after the std work
+            reserved = true;
+        }
         if (remain < n) {
             // keep only the `remain` closest members (remain_reads_ratio < 1)
             K128* R = A.A0;
@@ -563,6 +733,14 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
         const double breakpointStart = (double)kept_pos_sum / (double)remain;
         const double signalLen = (double)kept_len_sum / (double)remain;
         // CIPOS / CILEN: np.std over the whole allele (:191-194); two lanes work concurrently
+#if defined(__CUDA_ARCH__)
+        if (Team::SIZE == 32) {  // warp team: 16 lanes share the two reductions (n <= 128 here)
+            auto g0 = [&](int i) { return (int64_t)D_pos[V3[st + i]]; };
+            auto g1 = [&](int i) { return (int64_t)D_len[V3[st + i]]; };
+            const double sd = warp_np_std2(g0, g1, n, sp, sl);
+            if (t == 0 || t == 8) red[t >> 3] = cal_cipos(sd, n, E.pow_half);
+        } else
+#endif
         if (Team::SIZE > 1) {
             if (t < 2) {  // lanes 0 / 1 run the SAME instruction stream on pos / len
                 const int32_t* src = t == 0 ? D_pos : D_len;
@@ -579,25 +757,26 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
         const int32_t cipos = (int32_t)red[0], cilen = (int32_t)red[1];
         tm.sync();
         int32_t pos_out = (int32_t)breakpointStart;
-        int32_t aux = 0;
         if (svtype == CSV_INS) {
-            // first member (allele order) whose sequence is long enough (:399-405)
-            const int32_t need = (int32_t)signalLen;
-            int64_t bi = INT64_MAX;
-            for (int i = t; i < n; i += Team::SIZE)
-                if (D_aux[V3[st + i]] >= need && i < bi) bi = i;
-            const int64_t pick = team_min(tm, bi, red);
-            if (pick == INT64_MAX) continue;  // ideal_ins_seq == '<INS>' -> dropped
-            pos_out = D_pos[V3[st + pick]];
-            aux = D_idx[V3[st + pick]];
+            if (!reserved) {  // remain < n: signalLen is only known now
+                const int32_t need = (int32_t)signalLen;
+                int64_t bi = INT64_MAX;
+                for (int i = t; i < n; i += Team::SIZE)
+                    if (D_aux[V3[st + i]] >= need && i < bi) bi = i;
+                const int64_t pick = team_min(tm, bi, red);
+                if (pick == INT64_MAX) continue;  // ideal_ins_seq == '<INS>' -> dropped
+                pos_pick = D_pos[V3[st + pick]];
+                aux = D_idx[V3[st + pick]];
+            }
+            pos_out = pos_pick;
             search = pos_out;
         }
-        uint32_t slot = 0, noff = 0;
         int64_t ok = 0;
         if (t == 0) {
             if ((uint32_t)n >= E.lim.pow_n) atomic_or_u32(&E.ctr->status, ST_POW_TABLE);
             atomic_max_u32(&E.ctr->max_support, (uint32_t)n);
-            ok = emit_reserve(E, (uint32_t)n, &slot, &noff) ? 1 : 0;
+            if (!reserved) emit_reserve_issue(E, (uint32_t)n, &slot, &noff);
+            ok = emit_reserve_check(E, (uint32_t)n, slot, noff) ? 1 : 0;
             red[0] = ok; red[1] = slot; red[2] = noff;
         }
         tm.sync();
@@ -656,7 +835,7 @@ CSV_HD int distinct_reads(Team tm, const SortedView& in, int64_t s, const uint64
     team_sort_u64(tm, kbuf, Mn);
     for (int i = t; i < n; i += Team::SIZE) F[i] = (i == 0 || hi32(kbuf[i]) != hi32(kbuf[i - 1])) ? 1u : 0u;
     tm.sync();
-    return (int)team_excl_scan(tm, F, n, red);
+    return (int)team_flag_scan(tm, F, n, red);
 }
 
 // sort members by (b, q) and split into sub-clusters where the b gap exceeds bias.
@@ -672,7 +851,7 @@ CSV_HD int split_on_b(Team tm, const SortedView& in, int64_t s, int m, int M, Ot
     };
     for (int i = t; i < m; i += Team::SIZE) A.F[i] = brk(i) ? 1u : 0u;
     tm.sync();
-    const int ns = (int)team_excl_scan(tm, A.F, m, red) + 1;
+    const int ns = (int)team_flag_scan(tm, A.F, m, red) + 1;
     for (int i = t; i < m; i += Team::SIZE)
         if (i == 0 || brk(i)) A.SUB[A.F[i] + (brk(i) ? 1u : 0u)] = (uint32_t)i;
     tm.sync();

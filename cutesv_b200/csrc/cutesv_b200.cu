@@ -155,6 +155,13 @@ struct csv_ctx {
         (ctx)->launches++;                                                             \
     } while (0)
 
+template <int KIND>
+static void launch_cluster_kind(csv_ctx* c, const TypeJob& J, const Emit& E, Counters* ctr, uint32_t* work, size_t smem_warp) {
+    LAUNCH(c, (k_cluster_warp<KIND>), c->n_sm * 3, CL_THREADS, smem_warp, J, E, ctr, work);
+    LAUNCH(c, (k_cluster_block<false, KIND>), c->n_sm, CL_THREADS, (size_t)BLOCK_M * ARENA_PER_MAX, J, E, ctr);
+    LAUNCH(c, (k_cluster_block<true, KIND>), c->n_sm, CL_THREADS, 0, J, E, ctr);
+}
+
 static int grid_for(const csv_ctx* c, int64_t n, int block, int per_sm = 8) {
     int64_t g = (n + block - 1) / block;
     int64_t cap = (int64_t)c->n_sm * per_sm;
@@ -276,9 +283,15 @@ extern "C" int csv_create(int device, void* stream, csv_ctx** out) {
     int rc = upload_tables(c, 1u << 16);
     if (rc != CSV_OK) { delete c; return rc; }
     // opt in to large dynamic shared memory for the cluster kernels
-    CU(cudaFuncSetAttribute(k_cluster_warp, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (CL_THREADS / 32) * WARP_M * ARENA_PER_MAX + (CL_THREADS / 32) * 40 * 8));
-    CU(cudaFuncSetAttribute(k_cluster_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
+    const int smem_warp = (CL_THREADS / 32) * WARP_M * ARENA_PER_MAX + (CL_THREADS / 32) * 40 * 8;
+    CU(cudaFuncSetAttribute(k_cluster_warp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
+    CU(cudaFuncSetAttribute(k_cluster_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
+    CU(cudaFuncSetAttribute(k_cluster_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
+    CU(cudaFuncSetAttribute(k_cluster_warp<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
+    CU(cudaFuncSetAttribute((k_cluster_block<false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
+    CU(cudaFuncSetAttribute((k_cluster_block<false, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
+    CU(cudaFuncSetAttribute((k_cluster_block<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
+    CU(cudaFuncSetAttribute((k_cluster_block<false, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
     *out = c;
     return CSV_OK;
 }
@@ -584,9 +597,12 @@ static int run_segment_and_cluster(csv_ctx* c, TypeJob& J, int t, uint32_t kslot
     const size_t smem_warp = (size_t)(CL_THREADS / 32) * WARP_M * ARENA_PER_MAX + (CL_THREADS / 32) * 40 * 8;
     if (c->ticket_next >= 1024) return set_err(CSV_E_STATE, "ticket pool exhausted");
     uint32_t* work = c->tickets.as<uint32_t>() + c->ticket_next++;  // zeroed per call
-    LAUNCH(c, k_cluster_warp, c->n_sm * 3, CL_THREADS, smem_warp, J, E, ctr, work);
-    LAUNCH(c, (k_cluster_block<false>), c->n_sm, CL_THREADS, (size_t)BLOCK_M * ARENA_PER_MAX, J, E, ctr);
-    LAUNCH(c, (k_cluster_block<true>), c->n_sm, CL_THREADS, 0, J, E, ctr);
+    switch (kind_of(t)) {   // one per-type routine per kernel instantiation (instruction-cache footprint)
+        case 0: launch_cluster_kind<0>(c, J, E, ctr, work, smem_warp); break;
+        case 1: launch_cluster_kind<1>(c, J, E, ctr, work, smem_warp); break;
+        case 2: launch_cluster_kind<2>(c, J, E, ctr, work, smem_warp); break;
+        default: launch_cluster_kind<3>(c, J, E, ctr, work, smem_warp); break;
+    }
     stage_end(c, CSV_ST_CLUSTER);
     return CSV_OK;
 }

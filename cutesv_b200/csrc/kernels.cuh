@@ -315,16 +315,16 @@ __global__ void k_other_gather(const int32_t* __restrict__ chrom, const int32_t*
 // ------------------------------------------------------------------------------------------
 // cluster kernels
 // ------------------------------------------------------------------------------------------
-template <class Team>
+// KIND selects the one per-type routine a kernel instantiation contains (0 INS/DEL, 1 DUP, 2 INV, 3 TRA):
+// one routine per kernel keeps the hot code inside the instruction cache.
+__host__ __device__ constexpr int kind_of(int svtype) { return (svtype == CSV_DEL || svtype == CSV_INS) ? 0 : svtype == CSV_DUP ? 1 : svtype == CSV_INV ? 2 : 3; }
+template <int KIND, class Team>
 __device__ __forceinline__ void run_cluster(Team tm, const TypeJob& J, int64_t s, int m, int M, char* arena, int64_t* red,
                                             uint32_t kslot, const Emit& E) {
-    switch (J.svtype) {
-        case CSV_DEL:
-        case CSV_INS: indel_cluster(tm, J.iv, s, m, M, arena, red, J.cp, J.svtype, kslot, E); break;
-        case CSV_DUP: dup_cluster(tm, J.sv, s, m, M, arena, red, J.cp, kslot, E); break;
-        case CSV_INV: inv_cluster(tm, J.sv, s, m, M, arena, red, J.cp, kslot, E); break;
-        default: tra_cluster(tm, J.sv, s, m, M, arena, red, J.cp, kslot, E); break;
-    }
+    if (KIND == 0) indel_cluster(tm, J.iv, s, m, M, arena, red, J.cp, J.svtype, kslot, E);
+    else if (KIND == 1) dup_cluster(tm, J.sv, s, m, M, arena, red, J.cp, kslot, E);
+    else if (KIND == 2) inv_cluster(tm, J.sv, s, m, M, arena, red, J.cp, kslot, E);
+    else tra_cluster(tm, J.sv, s, m, M, arena, red, J.cp, kslot, E);
 }
 __device__ __forceinline__ int arena_per(const TypeJob& J) {
     return (J.svtype == CSV_DEL || J.svtype == CSV_INS) ? INDEL_ARENA_PER : OTHER_ARENA_PER;
@@ -346,6 +346,7 @@ __device__ __forceinline__ int cluster_size_warp(const TypeJob& J, int64_t s, in
 }
 
 // one warp per kept cluster; clusters larger than WARP_M are deferred to the CTA kernel
+template <int KIND>
 __global__ void __launch_bounds__(CL_THREADS) k_cluster_warp(TypeJob J, Emit E, Counters* ctr, uint32_t* work) {
     extern __shared__ __align__(16) char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -356,11 +357,14 @@ __global__ void __launch_bounds__(CL_THREADS) k_cluster_warp(TypeJob J, Emit E, 
     const uint32_t n_kept = ctr->n_kept[J.svtype];
     CudaTeam<32> tm;
     // dynamic hand-out (one atomic per cluster): cluster costs vary, a static stride leaves a long tail
+    // (the ticket of the NEXT cluster is requested before the current one is processed, so the atomic's round
+    //  trip overlaps the work)
+    uint32_t k_next = 0;
+    if (lane == 0) k_next = atomicAdd(work, 1u);
     while (true) {
-        uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(work, 1u);
-        k = __shfl_sync(0xffffffffu, k, 0);
+        const uint32_t k = __shfl_sync(0xffffffffu, k_next, 0);
         if (k >= n_kept) break;
+        if (lane == 0) k_next = atomicAdd(work, 1u);
         const int64_t s = J.kept_start[k];
         const int m = cluster_size_warp(J, s, n, WARP_M);
         if (m > WARP_M) {
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(CL_THREADS) k_cluster_warp(TypeJob J, Emit E, 
             continue;
         }
         if (lane == 0) atomicAdd(&ctr->n_members[J.svtype], (uint32_t)m);
-        run_cluster(tm, J, s, m, pow2ceil(m), arena, red, J.kslot_base + k, E);
+        run_cluster<KIND>(tm, J, s, m, pow2ceil(m), arena, red, J.kslot_base + k, E);
         __syncwarp();
     }
 }
@@ -390,7 +394,7 @@ __device__ __forceinline__ int64_t cluster_size_block(const TypeJob& J, int64_t 
 }
 
 // one CTA per deferred cluster; GIANT = arena in global scratch instead of shared memory
-template <bool GIANT>
+template <bool GIANT, int KIND>
 __global__ void __launch_bounds__(CL_THREADS) k_cluster_block(TypeJob J, Emit E, Counters* ctr) {
     extern __shared__ __align__(16) char smem[];
     __shared__ int64_t red[CL_THREADS + 8];
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(CL_THREADS) k_cluster_block(TypeJob J, Emit E,
         if (threadIdx.x == 0) atomicAdd(&ctr->n_members[J.svtype], (uint32_t)m);
         // global scratch: clusters are disjoint ranges of the sorted order and M <= 2m
         char* arena = GIANT ? (J.giant_arena + (size_t)(2 * s) * ARENA_PER_MAX) : smem;
-        run_cluster(tm, J, s, (int)m, M, arena, red, J.kslot_base + k, E);
+        run_cluster<KIND>(tm, J, s, (int)m, M, arena, red, J.kslot_base + k, E);
         __syncthreads();
     }
 }
