@@ -87,6 +87,20 @@ static void extract_release(ExtractState* x) {
     x->h_counters = nullptr;
 }
 
+// Lanes: SV types are independent until the `order` stage, so their kernel chains run concurrently on
+// separate streams (one lane per SV type; DEL uses the ctx stream).
+// Each lane owns the scratch its chain mutates; the buffers are swapped into the ctx while the lane's
+// launches are being enqueued (see csv_cluster).
+struct LaneWork {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_join = nullptr;
+    bool used = false;
+    DBuf keys_a, keys_b, vals_a, vals_b, hist, lb_status, bkt, bkt_flags, big_list, giant_list, giant_arena;
+    SmallWork small;
+};
+static constexpr int N_LANES = CSV_NTYPES;
+static inline int lane_of(int t) { return t; }
+
 struct csv_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -120,6 +134,9 @@ struct csv_ctx {
     uint32_t gen = 1;
     int ticket_next = 0;
     SmallWork small;
+    LaneWork lanes[N_LANES - 1];   // lane 0 = the ctx's own stream and buffers
+    cudaEvent_t ev_fork = nullptr;
+    bool lanes_enabled = true;
     // segment / cluster
     DBuf kept[CSV_NTYPES], big_list, giant_list, giant_arena, cnt;
     uint32_t kept_cap[CSV_NTYPES] = {0, 0, 0, 0, 0};
@@ -272,11 +289,17 @@ extern "C" int csv_create(int device, void* stream, csv_ctx** out) {
         cudaError_t e4 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
         for (int i = 0; i <= CSV_NTYPES && e4 == cudaSuccess; i++) e4 = cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming);
         if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
-        if (e4 != cudaSuccess) { delete c; return set_err(CSV_E_CUDA, "copy stream: %s", cudaGetErrorString(e4)); }
+        if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+        for (int l = 0; l < N_LANES - 1 && e4 == cudaSuccess; l++) {
+            e4 = cudaStreamCreateWithFlags(&c->lanes[l].stream, cudaStreamNonBlocking);
+            if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->lanes[l].ev_join, cudaEventDisableTiming);
+        }
+        if (e4 != cudaSuccess) { delete c; return set_err(CSV_E_CUDA, "copy stream / lanes: %s", cudaGetErrorString(e4)); }
     }
     csv_default_params(&c->P);
     if (const char* e = getenv("CUTESV_B200_PAIR_CAP")) c->pair_cap_override = atoll(e);
     if (const char* e = getenv("CUTESV_B200_NO_PREFILTER")) c->prefilter_enabled = atoi(e) == 0;
+    if (const char* e = getenv("CUTESV_B200_LANES")) c->lanes_enabled = atoi(e) != 0;
     for (int s = 0; s < CSV_ST_COUNT; s++) c->stage_ms[s] = 0.f;
     cudaError_t e3 = cudaMallocHost((void**)&c->h_counters, sizeof(Counters));
     if (e3 != cudaSuccess) { delete c; return set_err(CSV_E_CUDA, "cudaMallocHost: %s", cudaGetErrorString(e3)); }
@@ -307,6 +330,16 @@ extern "C" int csv_destroy(csv_ctx* c) {
                    &c->small.perm_a, &c->small.perm_b, &c->small.sel, &c->small.u_chrom, &c->small.u_a, &c->small.u_b,
                    &c->small.u_rid, &c->small.u_c};
     for (DBuf* b : all) b->release();
+    for (int l = 0; l < N_LANES - 1; l++) {
+        LaneWork& L = c->lanes[l];
+        if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
+        if (L.ev_join) cudaEventDestroy(L.ev_join);
+        DBuf* lb[] = {&L.keys_a, &L.keys_b, &L.vals_a, &L.vals_b, &L.hist, &L.lb_status, &L.bkt, &L.bkt_flags, &L.big_list, &L.giant_list, &L.giant_arena,
+                      &L.small.k_rid, &L.small.k_b, &L.small.k_prim, &L.small.perm_a, &L.small.perm_b, &L.small.sel, &L.small.u_chrom, &L.small.u_a,
+                      &L.small.u_b, &L.small.u_rid, &L.small.u_c};
+        for (DBuf* b : lb) b->release();
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int t = 0; t < CSV_NTYPES; t++) {
         c->sig[t].chrom.release(); c->sig[t].a.release(); c->sig[t].b.release(); c->sig[t].rid.release(); c->sig[t].c.release();
         c->kept[t].release();
@@ -728,6 +761,29 @@ static int run_other(csv_ctx* c, int t, uint32_t kslot_base) {
     return run_segment_and_cluster(c, J, t, kslot_base);
 }
 
+static void lane_swap(csv_ctx* c, LaneWork& L) {
+    std::swap(c->stream, L.stream);
+    std::swap(c->keys_a, L.keys_a); std::swap(c->keys_b, L.keys_b); std::swap(c->vals_a, L.vals_a); std::swap(c->vals_b, L.vals_b);
+    std::swap(c->hist, L.hist); std::swap(c->lb_status, L.lb_status); std::swap(c->bkt, L.bkt); std::swap(c->bkt_flags, L.bkt_flags);
+    std::swap(c->big_list, L.big_list); std::swap(c->giant_list, L.giant_list); std::swap(c->giant_arena, L.giant_arena);
+    std::swap(c->small, L.small);
+}
+static int ensure_small(csv_ctx* c, size_t ns) {
+    SmallWork& w = c->small;
+    CU(w.k_rid.ensure(ns * 4)); CU(w.k_b.ensure(ns * 4)); CU(w.k_prim.ensure(ns * 8)); CU(w.perm_a.ensure(ns * 4)); CU(w.perm_b.ensure(ns * 4));
+    CU(w.sel.ensure(ns * 4)); CU(w.u_chrom.ensure(ns * 4)); CU(w.u_a.ensure(ns * 4)); CU(w.u_b.ensure(ns * 4)); CU(w.u_rid.ensure(ns * 4));
+    CU(w.u_c.ensure(ns * 4));
+    return CSV_OK;
+}
+// scratch of the lane currently swapped into the ctx, for chains over at most nm signatures
+static int ensure_lane_scratch(csv_ctx* c, size_t nm) {
+    CU(c->keys_a.ensure(nm * 8)); CU(c->keys_b.ensure(nm * 8)); CU(c->vals_a.ensure(nm * 4)); CU(c->vals_b.ensure(nm * 4));
+    CU(c->big_list.ensure((nm / WARP_M + 2) * 4));
+    CU(c->giant_list.ensure((nm / BLOCK_M + 2) * 4));
+    CU(c->giant_arena.ensure(nm * 2 * ARENA_PER_MAX + 256));
+    return CSV_OK;
+}
+
 static int ensure_workspace(csv_ctx* c, uint32_t type_mask) {
     int64_t n_max = 0, n_total = 0, n_small_max = 0;
     for (int t = 0; t < CSV_NTYPES; t++) {
@@ -737,14 +793,26 @@ static int ensure_workspace(csv_ctx* c, uint32_t type_mask) {
         if (t >= CSV_INV) n_small_max = std::max(n_small_max, c->sig[t].n);
     }
     const size_t nm = (size_t)std::max<int64_t>(n_max, 1);
-    CU(c->keys_a.ensure(nm * 8)); CU(c->keys_b.ensure(nm * 8)); CU(c->vals_a.ensure(nm * 4)); CU(c->vals_b.ensure(nm * 4));
+    int rc0 = ensure_lane_scratch(c, nm);   // lane 0 can run every type (lanes disabled / profiling)
+    if (rc0) return rc0;
+    if (c->lanes_enabled) {
+        for (int l = 1; l < N_LANES; l++) {
+            int64_t nl = 0;
+            for (int t = 0; t < CSV_NTYPES; t++)
+                if ((type_mask >> t & 1) && lane_of(t) == l) nl = std::max(nl, c->sig[t].n);
+            if (nl == 0) continue;
+            LaneWork& L = c->lanes[l - 1];
+            lane_swap(c, L);
+            int rcl = ensure_lane_scratch(c, (size_t)nl);
+            if (!rcl && l >= CSV_INV) rcl = ensure_small(c, (size_t)nl);
+            lane_swap(c, L);
+            if (rcl) return rcl;
+        }
+    }
     CU(c->tickets.ensure(1024 * 4));
     CU(c->counters.ensure(sizeof(Counters)));
-    const size_t ns = (size_t)std::max<int64_t>(n_small_max, 1);
-    SmallWork& w = c->small;
-    CU(w.k_rid.ensure(ns * 4)); CU(w.k_b.ensure(ns * 4)); CU(w.k_prim.ensure(ns * 8)); CU(w.perm_a.ensure(ns * 4)); CU(w.perm_b.ensure(ns * 4));
-    CU(w.sel.ensure(ns * 4)); CU(w.u_chrom.ensure(ns * 4)); CU(w.u_a.ensure(ns * 4)); CU(w.u_b.ensure(ns * 4)); CU(w.u_rid.ensure(ns * 4));
-    CU(w.u_c.ensure(ns * 4));
+    rc0 = ensure_small(c, (size_t)std::max<int64_t>(n_small_max, 1));
+    if (rc0) return rc0;
     uint64_t kept_total = 0;
     const int ms = std::max(1, c->P.min_support);
     for (int t = 0; t < CSV_NTYPES; t++) {
@@ -754,9 +822,6 @@ static int ensure_workspace(csv_ctx* c, uint32_t type_mask) {
         kept_total += c->kept_cap[t];
     }
     CU(c->cnt.ensure((size_t)kept_total * 4 + 4));
-    CU(c->big_list.ensure((nm / WARP_M + 2) * 4));
-    CU(c->giant_list.ensure((nm / BLOCK_M + 2) * 4));
-    CU(c->giant_arena.ensure(nm * 2 * ARENA_PER_MAX + 256));
     const int ms_a = std::max(1, std::min(c->P.min_support, std::max(1, c->P.min_support_allele)));
     c->cap_cand = (uint32_t)(2 * (n_total / ms_a) + 16);  // TRA can emit two rows per chain cluster (resolveTRA.py:133-209)
     c->cap_names = (uint32_t)(n_total + 16);
@@ -784,13 +849,28 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
     CU(cudaMemsetAsync(c->cnt.p, 0, c->cnt.cap, c->stream));
     Counters* ctr = c->counters.as<Counters>();
     uint32_t kslot_base = 0;
+    // fork: every lane's chain starts after the resets above; join before `order`
+    const bool lanes = c->lanes_enabled;
+    if (lanes) CU(cudaEventRecord(c->ev_fork, c->stream));
+    for (int l = 0; l < N_LANES - 1; l++) c->lanes[l].used = false;
     for (int t = 0; t < CSV_NTYPES; t++) {
         if (!(type_mask >> t & 1) || c->sig[t].n == 0) continue;
+        LaneWork* L = (lanes && lane_of(t) > 0) ? &c->lanes[lane_of(t) - 1] : nullptr;
+        if (L) {
+            if (!L->used) { CU(cudaStreamWaitEvent(L->stream, c->ev_fork, 0)); L->used = true; }
+            lane_swap(c, *L);   // c->stream and the scratch buffers are the lane's until swapped back
+        }
         rc = wait_upload(c, t);
-        if (rc) return rc;
-        rc = (t == CSV_DEL || t == CSV_INS) ? run_indel(c, t, kslot_base) : run_other(c, t, kslot_base);
+        if (!rc) rc = (t == CSV_DEL || t == CSV_INS) ? run_indel(c, t, kslot_base) : run_other(c, t, kslot_base);
+        if (L) lane_swap(c, *L);
         if (rc) return rc;
         kslot_base += c->kept_cap[t];
+    }
+    for (int l = 0; l < N_LANES - 1; l++) {
+        LaneWork& L = c->lanes[l];
+        if (!L.used) continue;
+        CU(cudaEventRecord(L.ev_join, L.stream));
+        CU(cudaStreamWaitEvent(c->stream, L.ev_join, 0));
     }
     // ---- order ----
     stage_begin(c, CSV_ST_ORDER);
