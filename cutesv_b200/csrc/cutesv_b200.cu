@@ -937,7 +937,7 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
         if (c->P.genotype && c->n_aln > 0 && (type_mask >> CSV_TRA & 1) && c->sig[CSV_TRA].n > 0) {
             AlnView A{c->a_chrom.as<int32_t>(), c->a_start.as<int32_t>(), c->a_end.as<int32_t>(), c->a_id.as<int32_t>(), c->a_prim.as<uint8_t>(),
                       c->a_off.as<uint32_t>(), c->a_span.as<int32_t>(), c->d_len.as<int64_t>()};
-            LAUNCH(c, k_tra_genotype, grid_for(c, c->cap_cand, 128, 4), 128, 0, G, A, c->P.bias_tra, c->P.gt_round);
+            LAUNCH(c, k_tra_genotype, c->n_sm * 8, 128, 0, G, A, c->P.bias_tra, c->P.gt_round);   // 4 warps per CTA, one warp per TRA candidate
         }
     }
     stage_end(c, CSV_ST_GENOTYPE);

@@ -625,15 +625,83 @@ __global__ void k_aln_fill(uint32_t* off, int32_t n_contigs, uint32_t n) {
             if (off[c] == 0xffffffffu) off[c] = off[c + 1];
     }
 }
-__global__ void k_tra_genotype(GenoJob G, AlnView A, int32_t bias, int32_t gt_round) {
+// Warp-cooperative count_coverage (core.h tra_count_coverage is the scalar statement the emulator runs):
+// 32 consecutive BAM-order records per step; the running counters become ballot prefix counts and the
+// record that triggers an early return is the lowest lane whose inclusive counts satisfy a return test.
+__device__ __forceinline__ int tra_count_coverage_warp(const AlnView& A, int32_t chr, int64_t s, int64_t e, const int32_t* sup, int n_sup,
+                                                       int32_t up_bound, int32_t itround, int32_t* nset, int32_t* dr, int64_t xs, int64_t xe) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t below = (1u << lane) - 1u, upto = below | (1u << lane);
+    int64_t iteration = 0, primary = 0;
+    const uint32_t lo0 = A.off[chr], hi0 = A.off[chr + 1];
+    uint32_t lo = lo0, hi = hi0;
+    const int64_t min_start = s - (int64_t)A.max_span[chr];
+    while (lo < hi) { uint32_t mid = lo + (hi - lo) / 2; if ((int64_t)A.start[mid] < min_start) lo = mid + 1; else hi = mid; }
+    for (uint32_t base = lo; base < hi0; base += 32) {
+        const uint32_t i = base + lane;
+        const bool valid = i < hi0;
+        const int64_t st = valid ? (int64_t)A.start[i] : 0, en = valid ? (int64_t)A.end[i] : 0;
+        const bool before_end = valid && st < e;                  // loop condition (starts ascend: a prefix of the lanes)
+        const bool fetched = before_end && en > s;
+        const bool prim = fetched && A.prim[i] != 0;
+        const bool spanning = prim && st < s && en > e;
+        const bool fresh = spanning && !(xs <= xe && st < xs && en > xe);
+        const bool is_ref = fresh && !sorted_contains(sup, n_sup, A.rid[i]);
+        const uint32_t m_f = __ballot_sync(0xffffffffu, fetched), m_p = __ballot_sync(0xffffffffu, prim);
+        const uint32_t m_n = __ballot_sync(0xffffffffu, fresh), m_r = __ballot_sync(0xffffffffu, is_ref);
+        const int64_t it_incl = iteration + __popc(m_f & upto), pr_incl = primary + __popc(m_p & upto);
+        const int32_t ns_incl = *nset + __popc(m_n & upto), dr_incl = *dr + __popc(m_r & upto);
+        const bool ret_up = spanning && ns_incl >= up_bound;       // return 1 inside the spanning block
+        const bool ret_round = prim && it_incl >= itround;         // the itround test is only reached by primary records
+        const uint32_t m_ret = __ballot_sync(0xffffffffu, ret_up || ret_round);
+        if (m_ret) {
+            const int src = __ffs(m_ret) - 1;
+            int code = ret_up ? 1 : (((double)pr_incl / (double)it_incl) <= 0.2 ? 1 : -1);
+            code = __shfl_sync(0xffffffffu, code, src);
+            *nset = __shfl_sync(0xffffffffu, ns_incl, src);
+            *dr = __shfl_sync(0xffffffffu, dr_incl, src);
+            return code;
+        }
+        iteration += __popc(m_f); primary += __popc(m_p);
+        *nset += __popc(m_n); *dr += __popc(m_r);
+        if (__ballot_sync(0xffffffffu, before_end) != 0xffffffffu) break;   // a record with start >= e (or the contig end) was seen
+    }
+    return 0;
+}
+// one warp per TRA candidate; the candidates are ordered by SV type, TRA last, so warp w takes candidate n-1-w
+__global__ void __launch_bounds__(128) k_tra_genotype(GenoJob G, AlnView A, int32_t bias, int32_t gt_round) {
     const uint32_t n = min(G.ctr->n_cand, G.cap_cand);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t w = warp; w < n; w += n_warps) {
+        const uint32_t i = n - 1 - w;
         const csv_cand c = G.cand[i];
-        if (c.svtype != CSV_TRA) continue;
+        if (c.svtype != CSV_TRA) break;   // uniform across the warp
+        const int32_t* sup = G.names + c.names_off;
+        const int32_t chr1 = c.chrom, chr2 = c.aux >> 2, n_sup = c.names_cnt;
+        const int32_t up = threshold_ref_count(n_sup);
+        int32_t nset = 0, dr = 0;
+        int64_t s = (int64_t)c.pos - bias; if (s < 0) s = 0;
+        int64_t e = (int64_t)c.pos + bias; if (e > A.contig_len[chr1]) e = A.contig_len[chr1];
+        const int st = tra_count_coverage_warp(A, chr1, s, e, sup, n_sup, up, gt_round, &nset, &dr, 1, 0);
+        const int64_t s1 = s, e1 = e;
         csv_geno g;
-        tra_call_gt(A, c, G.names + c.names_off, bias, gt_round, G.gl_table, &g);
-        G.geno[i] = g;
-        G.cand[i].flags = c.flags & ~CSV_F_GT_HOST;
+        if (st == -1) {  // DR '.', GT './.' (resolveTRA.py:277-282)
+            g.dr = -1; g.dv = n_sup; g.gt = -1; g.pl[0] = g.pl[1] = g.pl[2] = 0; g.gq = 0; g.status = 2; g.qual = 0.0;
+        } else {
+            if (st == 0) {
+                s = (int64_t)c.pos2 - bias; if (s < 0) s = 0;
+                e = (int64_t)c.pos2 + bias; if (e > A.contig_len[chr2]) e = A.contig_len[chr2];
+                if (chr2 == chr1) tra_count_coverage_warp(A, chr2, s, e, sup, n_sup, up, gt_round, &nset, &dr, s1, e1);
+                else tra_count_coverage_warp(A, chr2, s, e, sup, n_sup, up, gt_round, &nset, &dr, 1, 0);
+            }
+            g = G.gl_table[gl_index(dr, n_sup)];
+            g.dr = dr; g.dv = n_sup;
+        }
+        if (lane == 0) {
+            G.geno[i] = g;
+            G.cand[i].flags = c.flags & ~CSV_F_GT_HOST;
+        }
     }
 }
 
