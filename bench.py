@@ -198,7 +198,15 @@ def main():
     reads_p = pinned_copy(torch, cfg["reads"])
     sigs_h = {k: {kk: vv for kk, vv in v.items() if not kk.startswith("_t_")} for k, v in sigs_p.items()}
     reads_h = {kk: vv for kk, vv in reads_p.items() if not kk.startswith("_t_")}
-    h2d = sum(v.nbytes for s in sigs_h.values() for v in s.values() if v is not None) + sum(v.nbytes for v in reads_h.values())
+    dev_in = sum(v.nbytes for s in sigs_h.values() for v in s.values() if v is not None) + sum(v.nbytes for v in reads_h.values())
+    # e2e inputs: the same rows grouped by contig (as the reference holds them: one list per chromosome, cuteSV:817-857)
+    # with row offsets instead of the 4-byte contig column (csv_cluster_host_grouped), in pinned host memory
+    n_contigs = len(cfg["lens"])
+    sigs_gp = {k: pinned_copy(torch, _abi.group_by_contig(v, n_contigs)) for k, v in cfg["sigs"].items()}
+    reads_gp = pinned_copy(torch, _abi.group_by_contig(cfg["reads"], n_contigs))
+    sigs_g = {k: {kk: vv for kk, vv in v.items() if not kk.startswith("_t_")} for k, v in sigs_gp.items()}
+    reads_g = {kk: vv for kk, vv in reads_gp.items() if not kk.startswith("_t_")}
+    h2d = sum(v.nbytes for s in sigs_g.values() for v in s.values() if v is not None) + sum(v.nbytes for v in reads_g.values())
     type_mask = sum(1 << _abi.TYPE_IDS[k] for k in cfg["sigs"])
 
     def barrier():
@@ -214,7 +222,6 @@ def main():
     for _ in range(max(args.warmup, 3)):
         eng.cluster_device(type_mask)
     n_cand, n_names = eng.counts()
-    eng.set_profiling(True)
     sampler = ClockSampler(local)
     sampler.start()
     l0 = eng.launch_count()
@@ -227,11 +234,28 @@ def main():
     barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
-    cands, genos, names = eng.fetch()  # also collects the per-stage events of the last step
-    stages = {k: v / args.steps for k, v in eng.stage_ms().items()}  # events accumulate over the timed steps
+    # ---------------- per-kernel durations: the same K steps with the SV-type lanes serialised ----------------
+    # (in the timed region above the kernel chains of the SV types overlap on separate streams, so a stage's
+    #  CUDA-event interval there includes time the GPU spent on another lane; the roofline of a KERNEL is taken
+    #  from this second pass, where every kernel runs alone on the ctx stream between its own events)
+    eng.set_lanes(False)
+    eng.set_profiling(True)
+    eng.cluster_device(type_mask)
+    eng.fetch()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for _ in range(args.steps):
+        eng.cluster_device(type_mask)
+    s1.record(stream)
+    barrier()
+    serial_ms = s0.elapsed_time(s1) / args.steps
+    cands, genos, names = eng.fetch()  # also collects the per-stage events
+    stages = {k: v / args.steps for k, v in eng.stage_ms().items()}  # events accumulate over the K steps
     probe = eng.sort_probe()
     ctrs = eng.counters()
     eng.set_profiling(False)
+    eng.set_lanes(True)
 
     # ---------------- end to end through the public call: e2e ----------------
     cap_c = max(2 * n_cand + 1024, 1024)
@@ -239,11 +263,11 @@ def main():
            torch.empty((2 * n_names + 1024) * 4, dtype=torch.uint8, pin_memory=True)]
     out = (pin[0].numpy().view(_abi.CAND_DTYPE), pin[1].numpy().view(_abi.GENO_DTYPE), pin[2].numpy().view(np.int32))
     for _ in range(max(args.warmup, 3)):
-        eng.cluster(sigs_h, reads_h, type_mask, out=out)
+        eng.cluster(sigs_g, reads_g, type_mask, out=out, grouped=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        c2, g2, n2 = eng.cluster(sigs_h, reads_h, type_mask, out=out)
+        c2, g2, n2 = eng.cluster(sigs_g, reads_g, type_mask, out=out, grouped=True)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -315,7 +339,8 @@ def main():
                        "scale": args.scale, "n_signatures_per_gpu": cfg["n_sigs"], "n_reads_per_gpu": int(len(cfg["reads"]["chrom"])),
                        "n_candidates": int(n_cand), "parallelism": ("contig-shard x%d (ONE genome, contigs LPT-packed over the GPUs)" if strong else
                                        "contig-shard x%d (one genome-equivalent of contigs per GPU)") % world,
-                       "l2": "inputs (%.0f MB/step) larger than the 126 MB L2, no explicit flush" % (h2d / 1e6),
+                       "l2": "inputs (%.0f MB/step) larger than the 126 MB L2, no explicit flush" % (dev_in / 1e6),
+                       "e2e_inputs": "host columns grouped by contig + row offsets (csv_cluster_host_grouped), pinned",
                        "allgather_ms": allgather_ms, "gathered_candidates": int(gathered_cands),
                        "density_filter_survivors": ctrs["domain"], "kept_clusters": ctrs["kept"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -326,11 +351,14 @@ def main():
                          "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes_per_step"] / max(kernels[dom]["launches_per_step"], 1),
                          "share_of_step": kernels[dom]["ms_per_step"] / max(dev_stage_sum, 1e-9),
+                         "timing": "CUDA events around the stage on the ctx stream, K steps with the SV-type lanes serialised "
+                                   "(%.4f ms/step; the timed region overlaps the lanes: %.4f ms/step)" % (serial_ms, dev_ms_max / args.steps),
                          "note": "dominant stage by CUDA-event time; it is latency/instruction bound, not DRAM bound (profiles/)"},
             "roofline_kernels": kernels,
             "roofline_pipeline": {"algorithmic_bytes_per_step": alg, "achieved": alg / 1e9 / (dev_ms_max / args.steps / 1e3), "unit": "GB/s",
                                   "frac": alg / 1e9 / (dev_ms_max / args.steps / 1e3) / peak},
             "stages_ms_per_step": stages,
+            "ms_per_step_lanes_serialised": serial_ms,
         }
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

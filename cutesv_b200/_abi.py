@@ -98,6 +98,41 @@ def make_sig_cols(cols):
     return csv_sig_cols(n, *[ptr(k) for k in keep]), keep
 
 
+def make_sig_cols_grouped(cols):
+    """cols: dict(contig_off, a, b, read_id[, c]) (rows grouped by contig) -> (struct, offsets array, keepalive)."""
+    if cols is None or len(cols["a"]) == 0:
+        return csv_sig_cols(0, None, None, None, None, None), None, ()
+    keep = tuple(i32(cols.get(k)) for k in ("a", "b", "read_id", "c"))
+    off = np.ascontiguousarray(cols["contig_off"], dtype=np.int64)
+    n = len(keep[0])
+    for k in keep:
+        assert k is None or len(k) == n
+    return csv_sig_cols(n, None, *[ptr(k) for k in keep]), off, keep + (off,)
+
+
+def make_reads_cols_grouped(reads):
+    if reads is None or len(reads["start"]) == 0:
+        return csv_reads_cols(0, None, None, None, None, None), None, ()
+    keep = [i32(reads[k]) for k in ("start", "end", "read_id")]
+    prim = np.ascontiguousarray(reads["is_primary"], dtype=np.uint8)
+    off = np.ascontiguousarray(reads["contig_off"], dtype=np.int64)
+    s = csv_reads_cols(len(keep[0]), None, *[ptr(k) for k in keep], ptr(prim, C.c_uint8))
+    return s, off, tuple(keep) + (prim, off)
+
+
+def group_by_contig(cols, n_contigs):
+    """Stable regrouping of a column dict by its `chrom` column: returns the dict without `chrom`, with
+    `contig_off` (n_contigs + 1 row offsets).  The order inside a contig is kept, so every tie-break on
+    the input order gives the same result as for the ungrouped columns."""
+    chrom = np.asarray(cols["chrom"])
+    order = np.argsort(chrom, kind="stable")
+    out = {k: (None if v is None else np.ascontiguousarray(np.asarray(v)[order])) for k, v in cols.items() if k != "chrom"}
+    off = np.zeros(n_contigs + 1, dtype=np.int64)
+    np.cumsum(np.bincount(chrom, minlength=n_contigs)[:n_contigs], out=off[1:])
+    out["contig_off"] = off
+    return out
+
+
 def make_reads_cols(reads):
     """reads: dict(chrom, start, end, read_id, is_primary) -> (struct, keepalive)."""
     if reads is None or len(reads["chrom"]) == 0:

@@ -29,6 +29,8 @@ _SIGNATURES = {
     "csv_host_unregister": (C.c_int, [_VP]),
     "csv_upload_sigs": (C.c_int, [_VP, C.c_int, C.POINTER(_abi.csv_sig_cols)]),
     "csv_upload_reads": (C.c_int, [_VP, C.POINTER(_abi.csv_reads_cols)]),
+    "csv_upload_sigs_grouped": (C.c_int, [_VP, C.c_int, C.POINTER(_abi.csv_sig_cols), _I64P]),
+    "csv_upload_reads_grouped": (C.c_int, [_VP, C.POINTER(_abi.csv_reads_cols), _I64P]),
     "csv_upload_alignments": (C.c_int, [_VP, C.POINTER(_abi.csv_reads_cols)]),
     "csv_cluster": (C.c_int, [_VP, C.c_uint32]),
     "csv_result_counts": (C.c_int, [_VP, _I64P, _I64P]),
@@ -36,6 +38,8 @@ _SIGNATURES = {
     "csv_result_device_ptrs": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     "csv_cluster_host": (C.c_int, [_VP, C.POINTER(_abi.csv_sig_cols), C.POINTER(_abi.csv_reads_cols), C.c_uint32, _VP, _VP,
                                    C.c_int64, _I32P, C.c_int64, _I64P, _I64P]),
+    "csv_cluster_host_grouped": (C.c_int, [_VP, C.POINTER(_abi.csv_sig_cols), C.POINTER(_I64P), C.POINTER(_abi.csv_reads_cols), _I64P,
+                                           C.c_uint32, _VP, _VP, C.c_int64, _I32P, C.c_int64, _I64P, _I64P]),
     "csv_cal_gl": (C.c_int, [_VP, _I32P, _I32P, C.c_int64, _VP]),
     "csv_extract": (C.c_int, [_VP, C.POINTER(_abi.csv_read_cols), C.POINTER(C.c_uint32), C.c_int64,
                               C.POINTER(_abi.csv_sa_cols), _I64P, _I64P]),
@@ -43,6 +47,7 @@ _SIGNATURES = {
     "csv_fetch_pieces": (C.c_int, [_VP, C.c_int64, _I32P, _I64P]),
     "csv_fetch_read_rows": (C.c_int, [_VP, C.c_int64, _I32P, _I32P, _I32P, _I32P, C.POINTER(C.c_uint8)]),
     "csv_set_profiling": (C.c_int, [_VP, C.c_int]),
+    "csv_set_lanes": (C.c_int, [_VP, C.c_int]),
     "csv_stage_ms": (C.c_int, [_VP, C.POINTER(C.c_float)]),
     "csv_launch_count": (C.c_int64, [_VP]),
     "csv_debug_counters": (C.c_int, [_VP, C.POINTER(C.c_uint32)]),

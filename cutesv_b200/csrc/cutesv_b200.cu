@@ -134,6 +134,7 @@ struct csv_ctx {
     uint32_t gen = 1;
     int ticket_next = 0;
     SmallWork small;
+    DBuf d_goff[CSV_NTYPES + 1];   // contig row offsets of grouped uploads (last: reads table)
     LaneWork lanes[N_LANES - 1];   // lane 0 = the ctx's own stream and buffers
     cudaEvent_t ev_fork = nullptr;
     bool lanes_enabled = true;
@@ -340,6 +341,7 @@ extern "C" int csv_destroy(csv_ctx* c) {
         for (DBuf* b : lb) b->release();
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int i = 0; i <= CSV_NTYPES; i++) c->d_goff[i].release();
     for (int t = 0; t < CSV_NTYPES; t++) {
         c->sig[t].chrom.release(); c->sig[t].a.release(); c->sig[t].b.release(); c->sig[t].rid.release(); c->sig[t].c.release();
         c->kept[t].release();
@@ -407,6 +409,12 @@ extern "C" int csv_host_free(void* p) { if (p) CU(cudaFreeHost(p)); return CSV_O
 extern "C" int csv_host_register(void* p, size_t bytes) { CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); return CSV_OK; }
 extern "C" int csv_host_unregister(void* p) { CU(cudaHostUnregister(p)); return CSV_OK; }
 
+extern "C" int csv_set_lanes(csv_ctx* c, int on) {
+    if (!c) return set_err(CSV_E_INVALID, "null ctx");
+    c->lanes_enabled = on != 0;
+    return CSV_OK;
+}
+
 extern "C" int csv_set_profiling(csv_ctx* c, int on) {
     if (!c) return set_err(CSV_E_INVALID, "null ctx");
     CU(cudaSetDevice(c->device));
@@ -432,7 +440,21 @@ static int wait_upload(csv_ctx* c, int slot) {
     }
     return CSV_OK;
 }
-extern "C" int csv_upload_sigs(csv_ctx* c, int t, const csv_sig_cols* h) {
+// Grouped uploads: rows grouped by contig id (ascending) + n_contigs+1 row offsets instead of the 4-byte contig
+// column; the column is rebuilt on the device behind the copies (k_expand_contigs on the copy stream).
+static int stage_group_offsets(csv_ctx* c, int slot, const int64_t* off, int64_t n, int32_t* chrom_dev) {
+    if (c->n_contigs == 0) return set_err(CSV_E_STATE, "csv_set_contigs has not been called");
+    if (off[0] != 0 || off[c->n_contigs] != n) return set_err(CSV_E_INVALID, "contig_off must start at 0 and end at n");
+    for (int k = 0; k < c->n_contigs; k++)
+        if (off[k + 1] < off[k]) return set_err(CSV_E_INVALID, "contig_off must be non-decreasing");
+    CU(c->d_goff[slot].ensure(((size_t)c->n_contigs + 1) * 8));
+    CU(cudaMemcpyAsync(c->d_goff[slot].p, off, ((size_t)c->n_contigs + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    k_expand_contigs<<<grid_for(c, n, 256 * 4), 256, 0, c->copy_stream>>>(c->d_goff[slot].as<int64_t>(), c->n_contigs, n, chrom_dev);
+    c->launches++;
+    return CSV_OK;
+}
+
+static int upload_sigs_impl(csv_ctx* c, int t, const csv_sig_cols* h, const int64_t* contig_off) {
     if (!c || t < 0 || t >= CSV_NTYPES || !h) return set_err(CSV_E_INVALID, "bad argument");
     if (h->n < 0 || h->n >= (1ll << 30)) return set_err(CSV_E_INVALID, "signature count %lld out of range", (long long)h->n);
     CU(cudaSetDevice(c->device));
@@ -441,13 +463,14 @@ extern "C" int csv_upload_sigs(csv_ctx* c, int t, const csv_sig_cols* h) {
     s.has_c = h->c != nullptr;
     c->counts_valid = false;
     if (h->n == 0) return CSV_OK;
-    if (!h->chrom || !h->a || !h->b || !h->read_id) return set_err(CSV_E_INVALID, "null column");
+    if ((!contig_off && !h->chrom) || !h->a || !h->b || !h->read_id) return set_err(CSV_E_INVALID, "null column");
     if ((t == CSV_INS || t == CSV_INV || t == CSV_TRA) && !h->c) return set_err(CSV_E_INVALID, "column c is required for INS/INV/TRA");
     const size_t bytes = (size_t)h->n * 4;
     int rc = upload_begin(c);
     if (rc) return rc;
     CU(s.chrom.ensure(bytes)); CU(s.a.ensure(bytes)); CU(s.b.ensure(bytes)); CU(s.rid.ensure(bytes));
-    CU(cudaMemcpyAsync(s.chrom.p, h->chrom, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    if (contig_off) { rc = stage_group_offsets(c, t, contig_off, h->n, s.chrom.as<int32_t>()); if (rc) return rc; }
+    else CU(cudaMemcpyAsync(s.chrom.p, h->chrom, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaMemcpyAsync(s.a.p, h->a, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaMemcpyAsync(s.b.p, h->b, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaMemcpyAsync(s.rid.p, h->read_id, bytes, cudaMemcpyHostToDevice, c->copy_stream));
@@ -456,21 +479,27 @@ extern "C" int csv_upload_sigs(csv_ctx* c, int t, const csv_sig_cols* h) {
     c->up_pending[t] = true;
     return CSV_OK;
 }
+extern "C" int csv_upload_sigs(csv_ctx* c, int t, const csv_sig_cols* h) { return upload_sigs_impl(c, t, h, nullptr); }
+extern "C" int csv_upload_sigs_grouped(csv_ctx* c, int t, const csv_sig_cols* h, const int64_t* contig_off) {
+    if (!contig_off) return set_err(CSV_E_INVALID, "null contig_off");
+    return upload_sigs_impl(c, t, h, contig_off);
+}
 
-extern "C" int csv_upload_reads(csv_ctx* c, const csv_reads_cols* h) {
+static int upload_reads_impl(csv_ctx* c, const csv_reads_cols* h, const int64_t* contig_off) {
     if (!c || !h) return set_err(CSV_E_INVALID, "bad argument");
     if (h->n < 0 || h->n >= (1ll << 31)) return set_err(CSV_E_INVALID, "read count out of range");
     CU(cudaSetDevice(c->device));
     c->n_reads = h->n;
     c->counts_valid = false;
     if (h->n == 0) return CSV_OK;
-    if (!h->chrom || !h->start || !h->end || !h->read_id || !h->is_primary) return set_err(CSV_E_INVALID, "null column");
+    if ((!contig_off && !h->chrom) || !h->start || !h->end || !h->read_id || !h->is_primary) return set_err(CSV_E_INVALID, "null column");
     const size_t bytes = (size_t)h->n * 4;
     int rc = upload_begin(c);
     if (rc) return rc;
     CU(c->r_chrom.ensure(bytes)); CU(c->r_start.ensure(bytes)); CU(c->r_end.ensure(bytes)); CU(c->r_id.ensure(bytes));
     CU(c->r_prim.ensure((size_t)h->n));
-    CU(cudaMemcpyAsync(c->r_chrom.p, h->chrom, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    if (contig_off) { rc = stage_group_offsets(c, CSV_NTYPES, contig_off, h->n, c->r_chrom.as<int32_t>()); if (rc) return rc; }
+    else CU(cudaMemcpyAsync(c->r_chrom.p, h->chrom, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaMemcpyAsync(c->r_start.p, h->start, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaMemcpyAsync(c->r_end.p, h->end, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaMemcpyAsync(c->r_id.p, h->read_id, bytes, cudaMemcpyHostToDevice, c->copy_stream));
@@ -478,6 +507,12 @@ extern "C" int csv_upload_reads(csv_ctx* c, const csv_reads_cols* h) {
     CU(cudaEventRecord(c->ev_up[CSV_NTYPES], c->copy_stream));
     c->up_pending[CSV_NTYPES] = true;
     return CSV_OK;
+}
+
+extern "C" int csv_upload_reads(csv_ctx* c, const csv_reads_cols* h) { return upload_reads_impl(c, h, nullptr); }
+extern "C" int csv_upload_reads_grouped(csv_ctx* c, const csv_reads_cols* h, const int64_t* contig_off) {
+    if (!contig_off) return set_err(CSV_E_INVALID, "null contig_off");
+    return upload_reads_impl(c, h, contig_off);
 }
 
 extern "C" int csv_upload_alignments(csv_ctx* c, const csv_reads_cols* h) {
@@ -1013,17 +1048,22 @@ extern "C" int csv_result_device_ptrs(csv_ctx* c, const csv_cand** cands, const 
     return CSV_OK;
 }
 
-extern "C" int csv_cluster_host(csv_ctx* c, const csv_sig_cols sigs[CSV_NTYPES], const csv_reads_cols* reads, uint32_t type_mask,
-                                csv_cand* cands, csv_geno* genos, int64_t cap_cand, int32_t* names, int64_t cap_names, int64_t* n_cand,
-                                int64_t* n_names) {
+static int cluster_host_impl(csv_ctx* c, const csv_sig_cols sigs[CSV_NTYPES], const int64_t* const* sig_off, const csv_reads_cols* reads,
+                             const int64_t* reads_off, bool grouped, uint32_t type_mask, csv_cand* cands, csv_geno* genos, int64_t cap_cand,
+                             int32_t* names, int64_t cap_names, int64_t* n_cand, int64_t* n_names) {
     if (!c || !sigs) return set_err(CSV_E_INVALID, "null argument");
     int rc;
     for (int t = 0; t < CSV_NTYPES; t++) {
         if (!(type_mask >> t & 1)) continue;
-        rc = csv_upload_sigs(c, t, &sigs[t]);
+        if (grouped && sigs[t].n > 0 && (!sig_off || !sig_off[t])) return set_err(CSV_E_INVALID, "null contig_off");
+        rc = upload_sigs_impl(c, t, &sigs[t], grouped && sigs[t].n > 0 ? sig_off[t] : nullptr);
         if (rc) return rc;
     }
-    if (reads) { rc = csv_upload_reads(c, reads); if (rc) return rc; }
+    if (reads) {
+        if (grouped && reads->n > 0 && !reads_off) return set_err(CSV_E_INVALID, "null contig_off");
+        rc = upload_reads_impl(c, reads, grouped && reads->n > 0 ? reads_off : nullptr);
+        if (rc) return rc;
+    }
     rc = csv_cluster(c, type_mask);
     if (rc) return rc;
     int64_t nc = 0, nn = 0;
@@ -1032,6 +1072,17 @@ extern "C" int csv_cluster_host(csv_ctx* c, const csv_sig_cols sigs[CSV_NTYPES],
     if (n_cand) *n_cand = nc;
     if (n_names) *n_names = nn;
     return csv_fetch(c, cands, genos, cap_cand, names, cap_names);
+}
+extern "C" int csv_cluster_host(csv_ctx* c, const csv_sig_cols sigs[CSV_NTYPES], const csv_reads_cols* reads, uint32_t type_mask,
+                                csv_cand* cands, csv_geno* genos, int64_t cap_cand, int32_t* names, int64_t cap_names, int64_t* n_cand,
+                                int64_t* n_names) {
+    return cluster_host_impl(c, sigs, nullptr, reads, nullptr, false, type_mask, cands, genos, cap_cand, names, cap_names, n_cand, n_names);
+}
+extern "C" int csv_cluster_host_grouped(csv_ctx* c, const csv_sig_cols sigs[CSV_NTYPES], const int64_t* const sig_off[CSV_NTYPES],
+                                        const csv_reads_cols* reads, const int64_t* reads_off, uint32_t type_mask, csv_cand* cands,
+                                        csv_geno* genos, int64_t cap_cand, int32_t* names, int64_t cap_names, int64_t* n_cand,
+                                        int64_t* n_names) {
+    return cluster_host_impl(c, sigs, sig_off, reads, reads_off, true, type_mask, cands, genos, cap_cand, names, cap_names, n_cand, n_names);
 }
 
 extern "C" int csv_cal_gl(csv_ctx* c, const int32_t* c0, const int32_t* c1, int64_t n, csv_geno* out) {

@@ -171,26 +171,65 @@ struct ContigTab {
 static constexpr int BKT_SHIFT = 8;   // 256 bp buckets
 static constexpr int BKT_PAD = 64;   // >= largest neighbourhood radius in buckets
 
+// grouped uploads: chrom[i] = the contig k with off[k] <= i < off[k+1] (four consecutive rows per thread)
+__global__ void __launch_bounds__(256) k_expand_contigs(const int64_t* __restrict__ off, int n_contigs, int64_t n, int32_t* __restrict__ chrom) {
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v * 4 < n; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = v * 4;
+        int lo = 0, hi = n_contigs;   // last k with off[k] <= i0
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(&off[mid]) <= i0) lo = mid; else hi = mid; }
+        int k = lo;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t i = i0 + j;
+            if (i >= n) break;
+            while (__ldg(&off[k + 1]) <= i) k++;   // skips empty contigs; off[n_contigs] == n > i ends it
+            chrom[i] = k;
+        }
+    }
+}
+
+// Four consecutive signatures per thread and iteration through 128-bit loads (64 B of loads in flight per
+// thread: the kernel is a latency-bound stream); a scalar loop takes the tail / unaligned columns.
 template <typename K, bool HIST>
-__global__ void k_indel_keys(const int32_t* __restrict__ chrom, const int32_t* __restrict__ a, const int32_t* __restrict__ b,
+__global__ void __launch_bounds__(256) k_indel_keys(const int32_t* __restrict__ chrom, const int32_t* __restrict__ a, const int32_t* __restrict__ b,
                              const int32_t* __restrict__ rid, int64_t n, int is_ins, ContigTab ct, K* __restrict__ keys,
                              uint32_t* status, uint32_t* __restrict__ bkt) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t c = chrom[i];
-        uint32_t bad = 0;
+    auto one = [&](int32_t c, int32_t raw, int32_t bb, int32_t rr, uint32_t& bad) -> K {
         K key = 0;
         if (c < 0 || c >= ct.n) bad |= ST_BAD_CHROM;
         else {
-            const int32_t raw = a[i];
             const int64_t pos = is_ins ? (raw >> 1) : raw;
             if (raw < 0 || pos > ct.len[c]) bad |= ST_BAD_POS;
             else key = (K)(ct.off[c] + (uint64_t)pos);
         }
-        if (rid[i] < 0 || b[i] < 0) bad |= ST_NEG_FIELD;
-        if (bad) atomicOr(status, bad);
+        if (rr < 0 || bb < 0) bad |= ST_NEG_FIELD;
+        return key;
+    };
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const bool aligned = ((((uintptr_t)chrom) | ((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)rid) | ((uintptr_t)keys)) & 15) == 0;
+    const int64_t nv = aligned ? (n >> 2) : 0;
+    uint32_t bad = 0;
+    for (int64_t v = tid; v < nv; v += stride) {
+        const int4 c4 = reinterpret_cast<const int4*>(chrom)[v], a4 = reinterpret_cast<const int4*>(a)[v];
+        const int4 b4 = reinterpret_cast<const int4*>(b)[v], r4 = reinterpret_cast<const int4*>(rid)[v];
+        const K k0 = one(c4.x, a4.x, b4.x, r4.x, bad), k1 = one(c4.y, a4.y, b4.y, r4.y, bad);
+        const K k2 = one(c4.z, a4.z, b4.z, r4.z, bad), k3 = one(c4.w, a4.w, b4.w, r4.w, bad);
+        if (sizeof(K) == 4) reinterpret_cast<uint4*>(keys)[v] = make_uint4((uint32_t)k0, (uint32_t)k1, (uint32_t)k2, (uint32_t)k3);
+        else {
+            reinterpret_cast<ulonglong2*>(keys)[2 * v] = make_ulonglong2((uint64_t)k0, (uint64_t)k1);
+            reinterpret_cast<ulonglong2*>(keys)[2 * v + 1] = make_ulonglong2((uint64_t)k2, (uint64_t)k3);
+        }
+        if (HIST) {
+            atomicAdd(&bkt[(uint32_t)(k0 >> BKT_SHIFT) + BKT_PAD], 1u); atomicAdd(&bkt[(uint32_t)(k1 >> BKT_SHIFT) + BKT_PAD], 1u);
+            atomicAdd(&bkt[(uint32_t)(k2 >> BKT_SHIFT) + BKT_PAD], 1u); atomicAdd(&bkt[(uint32_t)(k3 >> BKT_SHIFT) + BKT_PAD], 1u);
+        }
+    }
+    for (int64_t i = nv * 4 + tid; i < n; i += stride) {
+        const K key = one(chrom[i], a[i], b[i], rid[i], bad);
         keys[i] = key;
         if (HIST) atomicAdd(&bkt[(uint32_t)(key >> BKT_SHIFT) + BKT_PAD], 1u);
     }
+    if (bad) atomicOr(status, bad);
 }
 
 // pass 2 of the density filter: one bit per bucket = "the +-rb bucket neighbourhood holds >= need

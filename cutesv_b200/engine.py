@@ -44,7 +44,12 @@ class Engine(object):
     def set_profiling(self, on):
         _lib.check(self.L.csv_set_profiling(self.h, int(bool(on))))
 
+    def set_lanes(self, on):
+        """Per-SV-type stream lanes (default on); off serialises the types on the ctx stream."""
+        _lib.check(self.L.csv_set_lanes(self.h, int(bool(on))))
+
     # -- device-resident path (bench `value`): upload once, cluster many times --
+
     def upload(self, sigs, reads):
         keep = []
         for t, name in enumerate(_abi.TYPE_NAMES):
@@ -81,18 +86,29 @@ class Engine(object):
         return cands[:nc], genos[:nc], names[:nn]
 
     # -- the reference-facing one-shot call: host columns in, host rows out --
-    def cluster(self, sigs, reads, type_mask=0x1F, out=None):
+    def cluster(self, sigs, reads, type_mask=0x1F, out=None, grouped=False):
         """sigs: {type_name: dict(chrom,a,b,read_id[,c])}; reads: dict(chrom,start,end,read_id,is_primary).
+        grouped=True: every dict holds rows grouped by contig and `contig_off` instead of `chrom`
+        (_abi.group_by_contig; csv_cluster_host_grouped).
         Returns (cands, genos, names) numpy arrays in the reference's emission order."""
         arr = (_abi.csv_sig_cols * _abi.CSV_NTYPES)()
+        offs = (C.POINTER(C.c_int64) * _abi.CSV_NTYPES)()
         keep = []
         total = 0
         for t, name in enumerate(_abi.TYPE_NAMES):
-            s, k = _abi.make_sig_cols(sigs.get(name))
+            if grouped:
+                s, off, k = _abi.make_sig_cols_grouped(sigs.get(name))
+                if off is not None:
+                    offs[t] = off.ctypes.data_as(C.POINTER(C.c_int64))
+            else:
+                s, k = _abi.make_sig_cols(sigs.get(name))
             arr[t] = s
             keep.append(k)
             total += s.n
-        r, rk = _abi.make_reads_cols(reads)
+        if grouped:
+            r, r_off, rk = _abi.make_reads_cols_grouped(reads)
+        else:
+            r, rk = _abi.make_reads_cols(reads)
         if out is None:
             cap_c = max(2 * (total // max(min(self.params.min_support_allele, self.params.min_support), 1)) + 16, 16)
             cap_n = total + 16
@@ -102,9 +118,13 @@ class Engine(object):
         else:
             cands, genos, names = out
         nc, nn = C.c_int64(0), C.c_int64(0)
-        _lib.check(self.L.csv_cluster_host(self.h, arr, C.byref(r), C.c_uint32(type_mask), cands.ctypes.data_as(C.c_void_p),
-                                           genos.ctypes.data_as(C.c_void_p), C.c_int64(len(cands)), _abi.ptr(names),
-                                           C.c_int64(len(names)), C.byref(nc), C.byref(nn)))
+        tail = (C.c_uint32(type_mask), cands.ctypes.data_as(C.c_void_p), genos.ctypes.data_as(C.c_void_p), C.c_int64(len(cands)),
+                _abi.ptr(names), C.c_int64(len(names)), C.byref(nc), C.byref(nn))
+        if grouped:
+            _lib.check(self.L.csv_cluster_host_grouped(self.h, arr, offs, C.byref(r),
+                                                       None if r_off is None else r_off.ctypes.data_as(C.POINTER(C.c_int64)), *tail))
+        else:
+            _lib.check(self.L.csv_cluster_host(self.h, arr, C.byref(r), *tail))
         return cands[:nc.value], genos[:nc.value], names[:nn.value]
 
     def cal_gl(self, c0, c1):

@@ -170,6 +170,13 @@ int csv_host_unregister(void* p);
  * async H2D copy of the columns onto the ctx stream.  n == 0 clears the type. */
 int csv_upload_sigs(csv_ctx* ctx, int svtype, const csv_sig_cols* host_cols);
 int csv_upload_reads(csv_ctx* ctx, const csv_reads_cols* host_cols);
+/* The same with rows GROUPED BY CONTIG, as the reference itself holds them (one list per chromosome:
+ * the <TYPE>.pickle / reads.pickle files are dicts keyed by chr, cuteSV:817-857): all rows of contig
+ * id 0, then id 1, ...; host_cols->chrom is ignored (may be NULL) and contig_off[k] .. contig_off[k+1]
+ * (n_contigs + 1 entries, contig_off[0] == 0, contig_off[n_contigs] == n) is the row range of contig k.
+ * Saves the 4-byte contig column on the PCIe link; the column is rebuilt on the device. */
+int csv_upload_sigs_grouped(csv_ctx* ctx, int svtype, const csv_sig_cols* host_cols, const int64_t* contig_off);
+int csv_upload_reads_grouped(csv_ctx* ctx, const csv_reads_cols* host_cols, const int64_t* contig_off);
 
 /* Optional input of the TRA genotyper: ALL alignment records (no mapq filter, every flag) in BAM
  * order, i.e. coordinate-sorted per contig, contigs ascending by id.  is_primary = flag in (0, 16).
@@ -201,6 +208,12 @@ int csv_result_device_ptrs(csv_ctx* ctx, const csv_cand** cands, const csv_geno*
 int csv_cluster_host(csv_ctx* ctx, const csv_sig_cols sigs[CSV_NTYPES], const csv_reads_cols* reads,
                      uint32_t type_mask, csv_cand* cands, csv_geno* genos, int64_t cap_cand,
                      int32_t* names, int64_t cap_names, int64_t* n_cand, int64_t* n_names);
+
+/* csv_cluster_host over grouped inputs (see csv_upload_sigs_grouped); sig_off[t] may be NULL when sigs[t].n == 0. */
+int csv_cluster_host_grouped(csv_ctx* ctx, const csv_sig_cols sigs[CSV_NTYPES], const int64_t* const sig_off[CSV_NTYPES],
+                             const csv_reads_cols* reads, const int64_t* reads_off, uint32_t type_mask, csv_cand* cands,
+                             csv_geno* genos, int64_t cap_cand, int32_t* names, int64_t cap_names, int64_t* n_cand,
+                             int64_t* n_names);
 
 /* cal_GL(c0=DR, c1=DV) (cuteSV_genotype.py:33-56) for n pairs, evaluated on the device. */
 int csv_cal_gl(csv_ctx* ctx, const int32_t* c0, const int32_t* c1, int64_t n, csv_geno* out);
@@ -255,6 +268,10 @@ int csv_fetch_read_rows(csv_ctx* ctx, int64_t cap, int32_t* chrom, int32_t* star
 /* Profiling: per-stage device milliseconds of the last csv_cluster / csv_extract call. */
 int csv_set_profiling(csv_ctx* ctx, int on);
 int csv_stage_ms(csv_ctx* ctx, float ms[CSV_ST_COUNT]);
+/* SV types are independent until the final ordering (the reference runs them as separate Pool#3
+ * tasks, cuteSV:1113-1199); by default each type's kernel chain runs on its own stream ("lane").
+ * on = 0 serialises the types on the ctx stream, e.g. to time every kernel alone. */
+int csv_set_lanes(csv_ctx* ctx, int on);
 /* Number of kernels the library launched since the ctx was created. */
 int64_t csv_launch_count(csv_ctx* ctx);
 /* Device counters of the last finished csv_cluster call, 32 words: [0] status, [1] candidates,

@@ -137,3 +137,84 @@ def test_genome_larger_than_4gbp_uses_64bit_keys(engine):
                           c=ln[ok] if name == "INS" else None)
     cfg = dict(lens=lens, sigs=sigs, reads=reads, params=dict(min_support=5, genotype=1))
     assert _run(engine, cfg) > 10
+
+
+def _expand(g):
+    """Grouped dict -> plain dict in the same (grouped) row order; `aux` of an INS row indexes these rows."""
+    out = {k: v for k, v in g.items() if k != "contig_off"}
+    out["chrom"] = np.repeat(np.arange(len(g["contig_off"]) - 1, dtype=np.int32), np.diff(g["contig_off"])).astype(np.int32)
+    return out
+
+
+def _grouped(cfg):
+    """(grouped sigs, grouped reads, the same rows as plain columns)."""
+    nc = len(cfg["lens"])
+    gs = {k: _abi.group_by_contig(v, nc) for k, v in cfg["sigs"].items()}
+    gr = _abi.group_by_contig(cfg["reads"], nc)
+    return gs, gr, {k: _expand(v) for k, v in gs.items()}, _expand(gr)
+
+
+@pytest.mark.parametrize("seed", [0, 3, 7, 11, 19])
+def test_grouped_inputs_adversarial(engine, seed):
+    """csv_cluster_host_grouped (rows grouped by contig + offsets, no contig column) == oracle on the plain columns."""
+    cfg = synth.adversarial(seed)
+    p = _abi.default_params(**cfg["params"])
+    engine.set_params(p)
+    engine.set_contigs(cfg["lens"])
+    gs, gr, ps, pr = _grouped(cfg)
+    got = engine.cluster(gs, gr, grouped=True)
+    ref = oracle_lib.cluster(p, cfg["lens"], ps, pr, n_threads=8)
+    d = compare_records.diff_records(ref, got)
+    assert not d, "\n".join(d[:5])
+    # grouping is stable inside a contig: apart from `aux` (a row index) the records equal those of the original order
+    ref0 = oracle_lib.cluster(p, cfg["lens"], cfg["sigs"], cfg["reads"], n_threads=8)
+    for f in ("svtype", "chrom", "pos", "len", "support", "cipos", "cilen", "names_cnt"):
+        assert np.array_equal(ref0[0][f], got[0][f]), f
+
+
+@pytest.mark.parametrize("cid,scale", [(2, 0.02), (3, 0.05)])
+def test_grouped_inputs_configs(engine, cid, scale):
+    cfg = synth.make_config(cid, scale)
+    p = _abi.default_params(**cfg["params"])
+    engine.set_params(p)
+    engine.set_contigs(cfg["lens"])
+    gs, gr, ps, pr = _grouped(cfg)
+    got = engine.cluster(gs, gr, grouped=True)
+    plain = engine.cluster(ps, pr)
+    assert not compare_records.diff_records(plain, got)
+    ref = oracle_lib.cluster(p, cfg["lens"], ps, pr, n_threads=8)
+    assert not compare_records.diff_records(ref, got)
+
+
+def test_grouped_bad_offsets(engine):
+    cfg = synth.make_config(2, 0.004)
+    engine.set_params(_abi.default_params(**cfg["params"]))
+    engine.set_contigs(cfg["lens"])
+    gs, gr, _, _ = _grouped(cfg)
+    bad = dict(gs["DEL"])
+    off = bad["contig_off"].copy()
+    off[-1] -= 1
+    bad["contig_off"] = off
+    with pytest.raises(RuntimeError):
+        engine.cluster({"DEL": bad, "INS": gs["INS"]}, gr, grouped=True)
+    off = gs["DEL"]["contig_off"].copy()
+    off[1], off[2] = off[2] + 1, off[1]
+    bad["contig_off"] = off
+    with pytest.raises(RuntimeError):
+        engine.cluster({"DEL": bad, "INS": gs["INS"]}, gr, grouped=True)
+    got = engine.cluster(gs, gr, grouped=True)   # the ctx still works afterwards
+    assert len(got[0]) > 0
+
+
+def test_lanes_off_same_records(engine):
+    """Per-type stream lanes on / off give identical records (order, genotypes, supporting reads)."""
+    cfg = synth.make_config(3, 0.05)
+    engine.set_params(_abi.default_params(**cfg["params"]))
+    engine.set_contigs(cfg["lens"])
+    a = engine.cluster(cfg["sigs"], cfg["reads"])
+    engine.set_lanes(False)
+    try:
+        b = engine.cluster(cfg["sigs"], cfg["reads"])
+    finally:
+        engine.set_lanes(True)
+    assert not compare_records.diff_records(a, b)
