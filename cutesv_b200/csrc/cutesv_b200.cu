@@ -870,6 +870,17 @@ static int ensure_workspace(csv_ctx* c, uint32_t type_mask) {
     return CSV_OK;
 }
 
+static int join_lanes(csv_ctx* c) {
+    for (int l = 0; l < N_LANES - 1; l++) {
+        LaneWork& L = c->lanes[l];
+        if (!L.used) continue;
+        CU(cudaEventRecord(L.ev_join, L.stream));
+        CU(cudaStreamWaitEvent(c->stream, L.ev_join, 0));
+        L.used = false;
+    }
+    return CSV_OK;
+}
+
 extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
     if (!c) return set_err(CSV_E_INVALID, "null ctx");
     if (c->n_contigs == 0) return set_err(CSV_E_STATE, "csv_set_contigs has not been called");
@@ -898,15 +909,11 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
         rc = wait_upload(c, t);
         if (!rc) rc = (t == CSV_DEL || t == CSV_INS) ? run_indel(c, t, kslot_base) : run_other(c, t, kslot_base);
         if (L) lane_swap(c, *L);
-        if (rc) return rc;
+        if (rc) { join_lanes(c); return rc; }   // the ctx stream must not run ahead of work already forked
         kslot_base += c->kept_cap[t];
     }
-    for (int l = 0; l < N_LANES - 1; l++) {
-        LaneWork& L = c->lanes[l];
-        if (!L.used) continue;
-        CU(cudaEventRecord(L.ev_join, L.stream));
-        CU(cudaStreamWaitEvent(c->stream, L.ev_join, 0));
-    }
+    rc = join_lanes(c);
+    if (rc) return rc;
     // ---- order ----
     stage_begin(c, CSV_ST_ORDER);
     {

@@ -20,6 +20,11 @@ for seed in (1, 34, 144):
 cfg = synth.make_config(2, 0.01)
 e.set_params(_abi.default_params(**cfg["params"])); e.set_contigs(cfg["lens"])
 n += len(e.cluster(cfg["sigs"], cfg["reads"])[0])
+# all five SV types on their stream lanes + the grouped-by-contig upload path
+cfg = synth.make_config(3, 0.02)
+e.set_params(_abi.default_params(**cfg["params"])); e.set_contigs(cfg["lens"])
+nc = len(cfg["lens"])
+n += len(e.cluster({k: _abi.group_by_contig(v, nc) for k, v in cfg["sigs"].items()}, _abi.group_by_contig(cfg["reads"], nc), grouped=True)[0])
 rng = np.random.default_rng(7)
 names, lens = synth.contigs(0.01)
 m = 700
