@@ -51,14 +51,28 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(ReadView R, const uint32
             int64_t q = -(int64_t)hard_l;
             // 128 CIGAR ops per warp iteration: every lane owns 4 consecutive ops, so one warp scan
             // (5 shuffle steps per offset) is amortised over 128 ops
+            // (the next 128 ops are requested before the current ones are scanned: with 24 resident warps per SM a
+            //  single 512 B request per warp is far too little in flight for HBM latency)
+            uint32_t nxt[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int64_t i = c_lo + lane * 4 + j;
+                nxt[j] = i < c_hi ? __ldg(&cigar[i]) : (uint32_t)OP_P;
+            }
             for (int64_t base = c_lo; base < c_hi; base += 128) {
                 int op[4];
                 int32_t len[4], radv[4], qadv[4];
                 int32_t r_tot = 0, q_tot = 0;
+                uint32_t cur[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const int64_t i = base + lane * 4 + j;
-                    const uint32_t cg = i < c_hi ? cigar[i] : (uint32_t)OP_P;
+                    cur[j] = nxt[j];
+                    const int64_t i = base + 128 + lane * 4 + j;
+                    nxt[j] = i < c_hi ? __ldg(&cigar[i]) : (uint32_t)OP_P;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t cg = cur[j];
                     op[j] = (int)(cg & 15);
                     len[j] = (int32_t)(cg >> 4);
                     radv[j] = op_ref_change(op[j]) ? len[j] : 0;     // cuteSV:633-643
