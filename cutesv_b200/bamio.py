@@ -48,6 +48,7 @@ def lib():
         L.bamr_ref_len.restype = C.c_int64
         L.bamr_set_chrom_ids.argtypes = [C.c_void_p, _I32P]
         L.bamr_keep_seq.argtypes = [C.c_void_p, C.c_int]
+        L.bamr_tune.argtypes = [C.c_void_p, C.c_int, C.c_int64]
         L.bamr_next.argtypes = [C.c_void_p, C.c_int64, C.POINTER(_Packet)]
         L.bamr_next.restype = C.c_int64
         L.bamr_n_names.argtypes = [C.c_void_p]
@@ -61,10 +62,11 @@ def lib():
     return _lib
 
 
-def _arr(ptr, n, dtype):
+def _arr(ptr, n, dtype, copy=True):
     if n == 0:
         return np.zeros(0, dtype=dtype)
-    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+    a = np.ctypeslib.as_array(ptr, shape=(n,))
+    return a.astype(dtype, copy=True) if copy else a
 
 
 def is_bam(path):
@@ -85,6 +87,10 @@ class BamReader(object):
         self.references = [L.bamr_ref_name(self._h, i).decode() for i in range(n)]
         self.lengths = [int(L.bamr_ref_len(self._h, i)) for i in range(n)]
         L.bamr_keep_seq(self._h, 1 if keep_seq else 0)
+
+    def tune(self, batch_blocks=0, headroom=-1):
+        """Chunking knobs (tests): BGZF blocks per chunk, bytes reserved in front of a chunk for a straddling record."""
+        lib().bamr_tune(self._h, int(batch_blocks), int(headroom))
 
     def close(self):
         if self._h:
@@ -108,24 +114,25 @@ class BamReader(object):
         ids = np.array([chrom_id.get(n, -1) for n in self.references], dtype=np.int32)
         lib().bamr_set_chrom_ids(self._h, ids.ctypes.data_as(_I32P))
 
-    def next_packet(self, max_records):
+    def next_packet(self, max_records, copy=True):
         """Next packet (dict like packing.pack_alignments + 'seq_off'/'seq4'), or None at EOF.
-        read_id holds provisional ids (first-seen order); see name_ranks()."""
+        read_id holds provisional ids (first-seen order); see name_ranks().
+        copy=False returns views of the decoder's own buffers, valid until the next call."""
         p = _Packet()
         n = lib().bamr_next(self._h, int(max_records), C.byref(p))
         if n < 0:
             raise IOError(lib().bamr_error().decode())
         if n == 0:
             return None
-        out = {k: _arr(getattr(p, k), n, np.int32) for k in ("chrom", "ref_start", "ref_end", "flag", "mapq", "query_len", "read_id")}
-        out["cigar_off"] = _arr(p.cigar_off, n + 1, np.int64)
-        out["sa_off"] = _arr(p.sa_off, n + 1, np.int64)
-        out["cigar"] = _arr(p.cigar, p.n_cigar, np.uint32)
-        out["sa"] = {k: _arr(getattr(p, "sa_" + s), p.n_sa, np.int32) for k, s in
+        out = {k: _arr(getattr(p, k), n, np.int32, copy) for k in ("chrom", "ref_start", "ref_end", "flag", "mapq", "query_len", "read_id")}
+        out["cigar_off"] = _arr(p.cigar_off, n + 1, np.int64, copy)
+        out["sa_off"] = _arr(p.sa_off, n + 1, np.int64, copy)
+        out["cigar"] = _arr(p.cigar, p.n_cigar, np.uint32, copy)
+        out["sa"] = {k: _arr(getattr(p, "sa_" + s), p.n_sa, np.int32, copy) for k, s in
                      (("chrom", "chrom"), ("pos0", "pos0"), ("strand", "strand"), ("mapq", "mapq"), ("first_clip", "first"),
                       ("last_clip", "last"), ("ref_span", "span"))}
-        out["seq_off"] = _arr(p.seq_off, n + 1, np.int64)
-        out["seq4"] = _arr(p.seq4, int(out["seq_off"][-1]), np.uint8)
+        out["seq_off"] = _arr(p.seq_off, n + 1, np.int64, copy)
+        out["seq4"] = _arr(p.seq4, int(out["seq_off"][-1]), np.uint8, copy)
         return out
 
     def names(self):

@@ -333,7 +333,7 @@ class _NativeSource(object):
             first_task.setdefault(chrom_id[t[0]], i)
         n_seen = 0
         while True:
-            pk = rd.next_packet(PACKET_READS)
+            pk = rd.next_packet(PACKET_READS, copy=False)   # views: everything kept beyond this iteration is copied below
             if pk is None:
                 break
             has_cigar = pk["cigar_off"][1:] > pk["cigar_off"][:-1]   # reference_end is None otherwise

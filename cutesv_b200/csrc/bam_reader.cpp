@@ -13,6 +13,8 @@
 
 #include <algorithm>
 #include <condition_variable>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -23,26 +25,36 @@ namespace {
 
 thread_local std::string g_err;
 
-struct Block { std::vector<uint8_t> comp; std::vector<uint8_t> raw; uint32_t isize; bool ok; };
+struct Block { std::vector<uint8_t> comp; uint8_t* dst; uint32_t isize; bool ok; };
 
 bool inflate_block(Block& b) {
-    b.raw.resize(b.isize);
     if (b.isize == 0) return true;
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
     if (inflateInit2(&zs, -15) != Z_OK) return false;
     zs.next_in = b.comp.data();
     zs.avail_in = (uInt)b.comp.size();
-    zs.next_out = b.raw.data();
-    zs.avail_out = (uInt)b.raw.size();
+    zs.next_out = b.dst;
+    zs.avail_out = (uInt)b.isize;
     int rc = inflate(&zs, Z_FINISH);
     inflateEnd(&zs);
     return rc == Z_STREAM_END && zs.total_out == b.isize;
 }
 
+// Decompressed bytes of one batch of BGZF blocks, inflated in place (no staging copy): [head, end) is valid
+// data; the HEADROOM bytes in front of the payload receive the tail of a record that started in the previous
+// chunk, so that every record is contiguous in exactly one chunk.
+static constexpr size_t HEADROOM_DEFAULT = 4u << 20;
+struct Chunk {
+    std::unique_ptr<uint8_t[]> mem;
+    uint8_t* head = nullptr;   // first valid byte
+    uint8_t* end = nullptr;
+};
+
 // A batch of BGZF blocks being inflated by the pool.
 struct Batch {
     std::vector<Block> blocks;
+    std::unique_ptr<Chunk> chunk;
     size_t next = 0, done = 0;   // guarded by Pool::m
 };
 
@@ -86,13 +98,63 @@ struct Pool {
     }
 };
 
+// Persistent fork-join workers for the record parser: run(n, fn) calls fn(0..n-1) on the pool and returns
+// when all are done.
+struct ForkJoin {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    std::function<void(int)> fn;
+    int n = 0, next = 0, done = 0;
+    uint64_t epoch = 0;
+    bool stop = false;
+    void start(int k) { for (int i = 0; i < k; i++) th.emplace_back([this]() { loop(); }); }
+    void loop() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv_work.wait(lk, [this]() { return stop || next < n; });
+            if (stop) return;
+            const int i = next++;
+            lk.unlock();
+            fn(i);
+            lk.lock();
+            if (++done == n) cv_done.notify_all();
+        }
+    }
+    void run(int count, std::function<void(int)> f) {
+        if (count <= 0) return;
+        if (th.empty()) { for (int i = 0; i < count; i++) f(i); return; }
+        std::unique_lock<std::mutex> lk(m);
+        fn = std::move(f); n = count; next = 0; done = 0;
+        cv_work.notify_all();
+        cv_done.wait(lk, [this]() { return done == n; });
+        n = 0; next = 0;
+    }
+    ~ForkJoin() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv_work.notify_all();
+        for (auto& t : th) t.join();
+    }
+};
+
+// variable-length output of one parser task (a contiguous range of records)
+struct ThreadOut {   // (CIGAR and sequence sizes are known from the fixed fields: those go straight to their final place)
+    std::vector<int32_t> sa_chrom, sa_pos0, sa_strand, sa_mapq, sa_first, sa_last, sa_span;
+    void clear() { sa_chrom.clear(); sa_pos0.clear(); sa_strand.clear(); sa_mapq.clear(); sa_first.clear(); sa_last.clear(); sa_span.clear(); }
+};
+
 struct Reader {
     FILE* f = nullptr;
     bool eof = false;            // no more blocks in the file
-    std::vector<uint8_t> buf;    // decompressed stream not yet consumed
-    size_t pos = 0;
+    std::vector<std::unique_ptr<Chunk>> chunks;   // chunks holding records of the packet being built; back() is current
+    const uint8_t* cur = nullptr;                 // read position inside chunks.back()
     int n_threads = 4;
+    int batch_blocks = 256;              // BGZF blocks per chunk
+    size_t headroom = HEADROOM_DEFAULT;
     Pool pool;
+    ForkJoin parsers;
+    std::vector<ThreadOut> touts;
+    std::vector<const uint8_t*> rec_ptr;   // start of every record of the packet being built
     Batch batch[2];              // [inflight] is being inflated while the parser consumes the other's payload
     int inflight = -1;
     std::string io_err;          // error met while reading ahead (reported when that batch is consumed)
@@ -148,48 +210,64 @@ bool read_blocks(Reader& r, Batch& b, int max_blocks) {
 // start inflating the next batch of the file (if any) in the background
 void prefetch(Reader& r) {
     if (r.inflight >= 0 || r.eof || !r.io_err.empty()) return;
-    const int slot = 0;  // batch[0] is always the in-flight one; its payload is moved into buf on arrival
-    read_blocks(r, r.batch[slot], 256);
-    if (r.batch[slot].blocks.empty()) return;
-    r.inflight = slot;
-    r.pool.submit(&r.batch[slot]);
+    Batch& b = r.batch[0];
+    read_blocks(r, b, r.batch_blocks);
+    if (b.blocks.empty()) return;
+    size_t total = 0;
+    for (auto& blk : b.blocks) total += blk.isize;
+    b.chunk.reset(new Chunk());
+    b.chunk->mem.reset(new uint8_t[r.headroom + total]);   // uninitialised on purpose
+    b.chunk->head = b.chunk->mem.get() + r.headroom;
+    b.chunk->end = b.chunk->head + total;
+    uint8_t* o = b.chunk->head;
+    for (auto& blk : b.blocks) { blk.dst = o; o += blk.isize; }
+    r.inflight = 0;
+    r.pool.submit(&b);
 }
 
-// append the payload of the next batch to r.buf; false at end of file or on error (g_err set)
-bool refill(Reader& r) {
-    if (r.pos > 0) {  // drop the consumed prefix
-        r.buf.erase(r.buf.begin(), r.buf.begin() + (long)r.pos);
-        r.pos = 0;
-    }
+// Makes the next chunk current, carrying the unread tail of the present one in front of it.
+// 1 ok, 0 clean end of file (nothing more to read), -1 error (g_err set).
+int next_chunk(Reader& r) {
     if (r.inflight < 0) prefetch(r);
     if (r.inflight < 0) {
-        if (!r.io_err.empty()) g_err = r.io_err;
-        return false;
+        if (!r.io_err.empty()) { g_err = r.io_err; return -1; }
+        return 0;
     }
     Batch& b = r.batch[r.inflight];
     r.pool.wait(&b);
-    size_t total = 0;
-    for (auto& blk : b.blocks) {
-        if (!blk.ok) { g_err = "BGZF inflate failed"; return false; }
-        total += blk.raw.size();
-    }
-    size_t o = r.buf.size();
-    r.buf.resize(o + total);
-    for (auto& blk : b.blocks) {
-        if (!blk.raw.empty()) memcpy(r.buf.data() + o, blk.raw.data(), blk.raw.size());
-        o += blk.raw.size();
-    }
+    for (auto& blk : b.blocks)
+        if (!blk.ok) { g_err = "BGZF inflate failed"; return -1; }
+    std::unique_ptr<Chunk> c = std::move(b.chunk);
     r.inflight = -1;
-    prefetch(r);   // the next batch inflates while the caller parses this one
-    return true;
+    const size_t carry = r.chunks.empty() ? 0 : (size_t)(r.chunks.back()->end - r.cur);
+    if (carry > (size_t)(c->head - c->mem.get())) {  // a record larger than the headroom: rebuild the chunk with room for it (rare)
+        const size_t total = (size_t)(c->end - c->head);
+        std::unique_ptr<Chunk> big(new Chunk());
+        big->mem.reset(new uint8_t[carry + total]);
+        big->head = big->mem.get() + carry;
+        big->end = big->head + total;
+        memcpy(big->head, c->head, total);
+        c = std::move(big);
+    }
+    if (carry) {
+        memcpy(c->head - carry, r.cur, carry);
+        c->head -= carry;
+        r.chunks.back()->end = const_cast<uint8_t*>(r.cur);   // those bytes now live in the new chunk
+    }
+    r.cur = c->head;
+    r.chunks.push_back(std::move(c));
+    prefetch(r);   // the following batch inflates while the caller works on this one
+    return 1;
 }
 
-// make sure `need` bytes are available at r.pos; false at clean EOF
-bool ensure(Reader& r, size_t need) {
-    while (r.buf.size() - r.pos < need) {
-        if (!refill(r)) return false;
+// `need` contiguous bytes at r.cur?  1 yes, 0 clean end of file, -1 error (g_err set)
+int ensure(Reader& r, size_t need) {
+    while (r.chunks.empty() || (size_t)(r.chunks.back()->end - r.cur) < need) {
+        g_err.clear();
+        const int st = next_chunk(r);
+        if (st <= 0) return st;
     }
-    return true;
+    return 1;
 }
 
 inline int32_t rd_i32(const uint8_t* p) { int32_t v; memcpy(&v, p, 4); return v; }
@@ -255,23 +333,22 @@ int bamr_open(const char* path, int n_threads, void** out) {
     if (!r->f) { g_err = std::string("cannot open ") + path; delete r; return -1; }
     r->n_threads = n_threads > 0 ? n_threads : 4;
     r->pool.start(r->n_threads);
+    if (r->n_threads > 1) r->parsers.start(r->n_threads);
     g_err.clear();
-    if (!ensure(*r, 12) || memcmp(r->buf.data() + r->pos, "BAM\1", 4) != 0) {
-        if (g_err.empty()) g_err = "not a BAM file";
-        fclose(r->f); delete r; return -1;
-    }
-    const int32_t l_text = rd_i32(r->buf.data() + r->pos + 4);
-    if (!ensure(*r, 12 + (size_t)l_text)) { g_err = "truncated BAM header"; fclose(r->f); delete r; return -1; }
-    r->pos += 8 + (size_t)l_text;
-    const int32_t n_ref = rd_i32(r->buf.data() + r->pos);
-    r->pos += 4;
+    auto fail = [&](const char* msg) { if (g_err.empty()) g_err = msg; fclose(r->f); r->f = nullptr; delete r; return -1; };
+    if (ensure(*r, 12) <= 0 || memcmp(r->cur, "BAM\1", 4) != 0) return fail("not a BAM file");
+    const int32_t l_text = rd_i32(r->cur + 4);
+    if (l_text < 0 || ensure(*r, 12 + (size_t)l_text) <= 0) return fail("truncated BAM header");
+    r->cur += 8 + (size_t)l_text;
+    const int32_t n_ref = rd_i32(r->cur);
+    r->cur += 4;
     for (int32_t i = 0; i < n_ref; i++) {
-        if (!ensure(*r, 4)) { g_err = "truncated BAM header"; fclose(r->f); delete r; return -1; }
-        const int32_t l_name = rd_i32(r->buf.data() + r->pos);
-        if (!ensure(*r, 4 + (size_t)l_name + 4)) { g_err = "truncated BAM header"; fclose(r->f); delete r; return -1; }
-        std::string nm((const char*)r->buf.data() + r->pos + 4, (size_t)l_name - 1);
-        const int32_t l_ref = rd_i32(r->buf.data() + r->pos + 4 + l_name);
-        r->pos += 8 + (size_t)l_name;
+        if (ensure(*r, 4) <= 0) return fail("truncated BAM header");
+        const int32_t l_name = rd_i32(r->cur);
+        if (l_name < 1 || ensure(*r, 4 + (size_t)l_name + 4) <= 0) return fail("truncated BAM header");
+        std::string nm((const char*)r->cur + 4, (size_t)l_name - 1);
+        const int32_t l_ref = rd_i32(r->cur + 4 + l_name);
+        r->cur += 8 + (size_t)l_name;
         r->ref_index[nm] = i;
         r->ref_name.push_back(nm);
         r->ref_len.push_back(l_ref);
@@ -293,64 +370,67 @@ const char* bamr_ref_name(void* h, int32_t i) { return ((Reader*)h)->ref_name[i]
 int64_t bamr_ref_len(void* h, int32_t i) { return ((Reader*)h)->ref_len[i]; }
 void bamr_set_chrom_ids(void* h, const int32_t* ids) { Reader* r = (Reader*)h; for (size_t i = 0; i < r->chrom_id.size(); i++) r->chrom_id[i] = ids[i]; }
 void bamr_keep_seq(void* h, int keep) { ((Reader*)h)->keep_seq = keep != 0; }
+// tests: BGZF blocks per chunk and the carry-over headroom (takes effect from the next chunk that is read)
+void bamr_tune(void* h, int batch_blocks, int64_t headroom) {
+    Reader* r = (Reader*)h;
+    if (batch_blocks > 0) r->batch_blocks = batch_blocks;
+    if (headroom >= 0) r->headroom = (size_t)headroom;
+}
 
-// Next packet of up to max_records MAPPED records (file order).  Returns the record count (0 at EOF,
-// -1 on error); pointers stay valid until the next call.
-int64_t bamr_next(void* h, int64_t max_records, bamr_packet* out) {
-    Reader& r = *(Reader*)h;
-    r.chrom.clear(); r.ref_start.clear(); r.ref_end.clear(); r.flag.clear(); r.mapq.clear(); r.query_len.clear(); r.read_id.clear();
-    r.cigar_off.assign(1, 0); r.sa_off.assign(1, 0); r.seq_off.assign(1, 0);
-    r.cigar.clear(); r.seq4.clear();
-    r.sa_chrom.clear(); r.sa_pos0.clear(); r.sa_strand.clear(); r.sa_mapq.clear(); r.sa_first.clear(); r.sa_last.clear(); r.sa_span.clear();
-    int64_t n = 0;
-    while (n < max_records) {
-        if (!ensure(r, 4)) break;
-        const int32_t block_size = rd_i32(r.buf.data() + r.pos);
-        if (block_size < 32) { g_err = "corrupt BAM record"; return -1; }
-        if (!ensure(r, 4 + (size_t)block_size)) { g_err = "truncated BAM record"; return -1; }
-        const uint8_t* p = r.buf.data() + r.pos + 4;
+// SA:Z and the long-CIGAR CG:B,I tag of a record (p = first byte after block_size)
+static void find_tags(const uint8_t* p, const uint8_t* end, const char** sa, const uint8_t** cg_tag, uint32_t* cg_cnt) {
+    const int l_read_name = p[8];
+    const int n_cigar = rd_u16(p + 12);
+    const int32_t l_seq = rd_i32(p + 16);
+    const uint8_t* aux = p + 32 + l_read_name + 4 * (size_t)n_cigar + (size_t)(l_seq + 1) / 2 + (size_t)l_seq;
+    *sa = nullptr; *cg_tag = nullptr; *cg_cnt = 0;
+    for (const uint8_t* a = aux; a + 3 <= end;) {
+        const char t0 = (char)a[0], t1 = (char)a[1], ty = (char)a[2];
+        const uint8_t* v = a + 3;
+        if (t0 == 'S' && t1 == 'A' && ty == 'Z') *sa = (const char*)v;
+        if (t0 == 'C' && t1 == 'G' && ty == 'B' && v + 5 <= end && (v[0] == 'I' || v[0] == 'i') && v + 5 + 4 * (size_t)rd_u32(v + 1) <= end) {
+            *cg_cnt = rd_u32(v + 1); *cg_tag = v + 5;
+        }
+        a = v + aux_skip(v, end, ty);
+    }
+}
+// a 2-op CIGAR "<l_seq>S<span>N" announces the real CIGAR in the CG tag (alignments with > 65535 ops)
+static inline bool cg_placeholder(const uint8_t* cg, int n_cigar, int32_t l_seq) {
+    return n_cigar == 2 && (rd_u32(cg) & 15) == 4 && (int32_t)(rd_u32(cg) >> 4) == l_seq && (rd_u32(cg + 4) & 15) == 3;
+}
+
+// Parses records [lo, hi) of r.rec_ptr: fixed-width fields straight into the packet columns (sized by the
+// caller), variable-length parts into `o`; per-record lengths go to cigar_off / sa_off / seq_off [k + 1].
+static void parse_range(Reader& r, size_t lo, size_t hi, ThreadOut& o) {
+    o.clear();
+    for (size_t k = lo; k < hi; k++) {
+        const uint8_t* p = r.rec_ptr[k] + 4;
+        const int32_t block_size = rd_i32(p - 4);
         const uint8_t* end = p + block_size;
-        r.pos += 4 + (size_t)block_size;
         const int32_t ref_id = rd_i32(p), pos = rd_i32(p + 4);
         const int l_read_name = p[8], mq = p[9];
         const int n_cigar = rd_u16(p + 12), flg = rd_u16(p + 14);
         const int32_t l_seq = rd_i32(p + 16);
-        if (ref_id < 0 || ref_id >= (int32_t)r.ref_name.size()) continue;  // unmapped / unplaced: never returned by fetch(chr, ...)
-        const char* qname = (const char*)p + 32;
         const uint8_t* cg = p + 32 + l_read_name;
         const uint8_t* sq = cg + 4 * (size_t)n_cigar;
-        const uint8_t* aux = sq + (size_t)(l_seq + 1) / 2 + (size_t)l_seq;
-        // tags: SA:Z and the long-CIGAR CG:B,I
-        const char* sa = nullptr;
-        const uint8_t* cg_tag = nullptr;
-        uint32_t cg_cnt = 0;
-        for (const uint8_t* a = aux; a + 3 <= end;) {
-            const char t0 = (char)a[0], t1 = (char)a[1], ty = (char)a[2];
-            const uint8_t* v = a + 3;
-            if (t0 == 'S' && t1 == 'A' && ty == 'Z') sa = (const char*)v;
-            if (t0 == 'C' && t1 == 'G' && ty == 'B' && v + 5 <= end && (v[0] == 'I' || v[0] == 'i')) { cg_cnt = rd_u32(v + 1); cg_tag = v + 5; }
-            a = v + aux_skip(v, end, ty);
-        }
+        const char* sa;
+        const uint8_t* cg_tag;
+        uint32_t cg_cnt;
+        find_tags(p, end, &sa, &cg_tag, &cg_cnt);
         const uint8_t* cig_src = cg;
         uint32_t cig_n = (uint32_t)n_cigar;
-        if (cg_tag && n_cigar == 2 && (rd_u32(cg) & 15) == 4 && (int32_t)(rd_u32(cg) >> 4) == l_seq && (rd_u32(cg + 4) & 15) == 3) {
-            cig_src = cg_tag; cig_n = cg_cnt;  // real CIGAR of a >65535-op alignment lives in the CG tag
-        }
+        if (cg_tag && cg_placeholder(cg, n_cigar, l_seq)) { cig_src = cg_tag; cig_n = cg_cnt; }
         int32_t span = 0;
-        for (uint32_t k = 0; k < cig_n; k++) {
-            const uint32_t c = rd_u32(cig_src + 4 * (size_t)k);
-            r.cigar.push_back(c);
+        uint32_t* cdst = r.cigar.data() + r.cigar_off[k];   // offsets were fixed by the scan phase
+        for (uint32_t j = 0; j < cig_n; j++) {
+            const uint32_t c = rd_u32(cig_src + 4 * (size_t)j);
+            cdst[j] = c;
             const int op = c & 15;
             if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += (int32_t)(c >> 4);
         }
-        r.cigar_off.push_back((int64_t)r.cigar.size());
-        std::string name(qname, (size_t)(l_read_name > 0 ? l_read_name - 1 : 0));
-        auto it = r.name_id.find(name);
-        int32_t id;
-        if (it == r.name_id.end()) { id = (int32_t)r.names.size(); r.name_id.emplace(name, id); r.names.push_back(name); }
-        else id = it->second;
-        r.chrom.push_back(r.chrom_id[ref_id]); r.ref_start.push_back(pos); r.ref_end.push_back(pos + span); r.flag.push_back(flg);
-        r.mapq.push_back(mq); r.query_len.push_back(l_seq); r.read_id.push_back(id);
+        r.chrom[k] = r.chrom_id[ref_id]; r.ref_start[k] = pos; r.ref_end[k] = pos + span; r.flag[k] = flg;
+        r.mapq[k] = mq; r.query_len[k] = l_seq;
+        const size_t s0 = o.sa_chrom.size();
         if (sa) {  // "rname,pos,strand,CIGAR,mapQ,NM;" ... (cuteSV:489-509)
             const char* s = sa;
             while (*s) {
@@ -363,21 +443,101 @@ int64_t bamr_next(void* h, int64_t max_records, bamr_packet* out) {
                     auto ri = r.ref_index.find(rn);
                     int32_t fc, lc, sp;
                     clip_pos(f[3], (size_t)(f[4] - f[3] - 1), &fc, &lc, &sp);
-                    r.sa_chrom.push_back(ri == r.ref_index.end() ? -1 : r.chrom_id[ri->second]);
-                    r.sa_pos0.push_back(atoi(f[1]) - 1);
-                    r.sa_strand.push_back(*f[2] == '+' ? 0 : 1);
-                    r.sa_mapq.push_back(atoi(f[4]));
-                    r.sa_first.push_back(fc); r.sa_last.push_back(lc); r.sa_span.push_back(sp);
+                    o.sa_chrom.push_back(ri == r.ref_index.end() ? -1 : r.chrom_id[ri->second]);
+                    o.sa_pos0.push_back(atoi(f[1]) - 1);
+                    o.sa_strand.push_back(*f[2] == '+' ? 0 : 1);
+                    o.sa_mapq.push_back(atoi(f[4]));
+                    o.sa_first.push_back(fc); o.sa_last.push_back(lc); o.sa_span.push_back(sp);
                 }
                 s = *e ? e + 1 : e;
             }
         }
-        r.sa_off.push_back((int64_t)r.sa_chrom.size());
-        if (r.keep_seq) r.seq4.insert(r.seq4.end(), sq, sq + (size_t)(l_seq + 1) / 2);
-        r.seq_off.push_back((int64_t)r.seq4.size());
-        n++;
+        r.sa_off[k + 1] = (int64_t)(o.sa_chrom.size() - s0);
+        if (r.keep_seq && l_seq > 0) memcpy(r.seq4.data() + r.seq_off[k], sq, (size_t)(l_seq + 1) / 2);
     }
-    out->n = n;
+}
+
+// Next packet of up to max_records MAPPED records (file order).  Returns the record count (0 at EOF,
+// -1 on error); pointers stay valid until the next call.
+// Three phases: (1) sequential hop over the block_size chain + read-name ids (first-seen order), (2) the
+// records are parsed by the fork-join pool in contiguous ranges, (3) the variable-length parts are stitched.
+int64_t bamr_next(void* h, int64_t max_records, bamr_packet* out) {
+    Reader& r = *(Reader*)h;
+    r.rec_ptr.clear();
+    r.read_id.clear();
+    r.cigar_off.assign(1, 0); r.seq_off.assign(1, 0);
+    if (r.chunks.size() > 1) r.chunks.erase(r.chunks.begin(), r.chunks.end() - 1);   // the previous packet's chunks
+    while ((int64_t)r.rec_ptr.size() < max_records) {
+        int st = ensure(r, 4);
+        if (st < 0) return -1;
+        if (st == 0) {
+            if (!r.chunks.empty() && r.chunks.back()->end > r.cur) { g_err = "truncated BAM record"; return -1; }
+            break;
+        }
+        const int32_t block_size = rd_i32(r.cur);
+        if (block_size < 32) { g_err = "corrupt BAM record"; return -1; }
+        st = ensure(r, 4 + (size_t)block_size);
+        if (st <= 0) { if (st == 0) g_err = "truncated BAM record"; return -1; }
+        const uint8_t* rec = r.cur;
+        const uint8_t* p = rec + 4;
+        const int32_t ref_id = rd_i32(p);
+        r.cur += 4 + (size_t)block_size;
+        if (ref_id < 0 || ref_id >= (int32_t)r.ref_name.size()) continue;  // unmapped / unplaced: never returned by fetch(chr, ...)
+        const int l_read_name = p[8];
+        {   // the fixed-size fields must describe a record that fits its block_size (the parser trusts them)
+            const int64_t n_cig = rd_u16(p + 12), l_seq = rd_i32(p + 16);
+            if (l_seq < 0 || 32 + (int64_t)l_read_name + 4 * n_cig + (l_seq + 1) / 2 + l_seq > (int64_t)block_size) {
+                g_err = "corrupt BAM record";
+                return -1;
+            }
+        }
+        std::string name((const char*)p + 32, (size_t)(l_read_name > 0 ? l_read_name - 1 : 0));
+        auto it = r.name_id.find(name);
+        int32_t id;
+        if (it == r.name_id.end()) { id = (int32_t)r.names.size(); r.name_id.emplace(name, id); r.names.push_back(std::move(name)); }
+        else id = it->second;
+        {   // sizes of the variable-length parts that the fixed fields (or, rarely, the CG tag) already tell
+            const int n_cig = rd_u16(p + 12);
+            const int32_t l_seq = rd_i32(p + 16);
+            int64_t cig_n = n_cig;
+            const uint8_t* cg = p + 32 + l_read_name;
+            if (cg_placeholder(cg, n_cig, l_seq)) {
+                const char* sa; const uint8_t* cg_tag; uint32_t cg_cnt;
+                find_tags(p, p + block_size, &sa, &cg_tag, &cg_cnt);
+                if (cg_tag) cig_n = cg_cnt;
+            }
+            r.cigar_off.push_back(r.cigar_off.back() + cig_n);
+            r.seq_off.push_back(r.seq_off.back() + (r.keep_seq ? (int64_t)((l_seq + 1) / 2) : 0));
+        }
+        r.rec_ptr.push_back(rec);
+        r.read_id.push_back(id);
+    }
+    const size_t n = r.rec_ptr.size();
+    r.chrom.resize(n); r.ref_start.resize(n); r.ref_end.resize(n); r.flag.resize(n); r.mapq.resize(n); r.query_len.resize(n);
+    r.sa_off.assign(n + 1, 0);
+    r.cigar.resize((size_t)r.cigar_off[n]); r.seq4.resize((size_t)r.seq_off[n]);
+    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)r.n_threads * 4, (n + 255) / 256));
+    if (r.touts.size() < (size_t)T) r.touts.resize((size_t)T);
+    auto range = [&](int t) { return std::make_pair(n * (size_t)t / (size_t)T, n * (size_t)(t + 1) / (size_t)T); };
+    r.parsers.run(T, [&](int t) { auto rg = range(t); parse_range(r, rg.first, rg.second, r.touts[(size_t)t]); });
+    // stitch: per-record lengths -> offsets; per-task blocks -> one array each
+    for (size_t k = 0; k < n; k++) r.sa_off[k + 1] += r.sa_off[k];
+    const size_t ns = n ? (size_t)r.sa_off[n] : 0;
+    r.sa_chrom.resize(ns); r.sa_pos0.resize(ns); r.sa_strand.resize(ns); r.sa_mapq.resize(ns); r.sa_first.resize(ns); r.sa_last.resize(ns); r.sa_span.resize(ns);
+    r.parsers.run(T, [&](int t) {
+        auto rg = range(t);
+        if (rg.first == rg.second) return;
+        const ThreadOut& o = r.touts[(size_t)t];
+        const size_t s0 = (size_t)r.sa_off[rg.first];
+        if (!o.sa_chrom.empty()) {
+            const size_t b = o.sa_chrom.size() * 4;
+            memcpy(r.sa_chrom.data() + s0, o.sa_chrom.data(), b); memcpy(r.sa_pos0.data() + s0, o.sa_pos0.data(), b);
+            memcpy(r.sa_strand.data() + s0, o.sa_strand.data(), b); memcpy(r.sa_mapq.data() + s0, o.sa_mapq.data(), b);
+            memcpy(r.sa_first.data() + s0, o.sa_first.data(), b); memcpy(r.sa_last.data() + s0, o.sa_last.data(), b);
+            memcpy(r.sa_span.data() + s0, o.sa_span.data(), b);
+        }
+    });
+    out->n = (int64_t)n;
     out->chrom = r.chrom.data(); out->ref_start = r.ref_start.data(); out->ref_end = r.ref_end.data(); out->flag = r.flag.data();
     out->mapq = r.mapq.data(); out->query_len = r.query_len.data(); out->read_id = r.read_id.data();
     out->cigar_off = r.cigar_off.data(); out->sa_off = r.sa_off.data();
@@ -386,7 +546,7 @@ int64_t bamr_next(void* h, int64_t max_records, bamr_packet* out) {
     out->sa_chrom = r.sa_chrom.data(); out->sa_pos0 = r.sa_pos0.data(); out->sa_strand = r.sa_strand.data(); out->sa_mapq = r.sa_mapq.data();
     out->sa_first = r.sa_first.data(); out->sa_last = r.sa_last.data(); out->sa_span = r.sa_span.data();
     out->seq_off = r.seq_off.data(); out->seq4 = r.seq4.data();
-    return n;
+    return (int64_t)n;
 }
 
 int64_t bamr_n_names(void* h) { return (int64_t)((Reader*)h)->names.size(); }

@@ -21,8 +21,10 @@ def _sorted_reads(seed, n_reads, with_seq=True):
     return reads, contigs
 
 
-def _read_all(path, chrom_id, chunk, **kw):
+def _read_all(path, chrom_id, chunk, tune=None, **kw):
     rd = bamio.BamReader(path, **kw)
+    if tune:
+        rd.tune(*tune)
     rd.set_chrom_ids(chrom_id)
     packets = []
     while True:
@@ -61,6 +63,26 @@ def test_packet_equals_python_packer(tmp_path, seed, chunk, via_cg):
     assert np.array_equal(rd.name_ranks()[:len(names)], rank) and sorted(names) == uniq
     assert rd.index_statistics() == [(nm, sum(1 for r in reads if r.reference_name == nm)) for nm, _ in contigs]
     rd.close()
+
+
+@pytest.mark.parametrize("tune", [(1, -1), (3, 64), (2, 0), (7, 5000)])
+def test_records_straddling_chunks(tmp_path, tune):
+    """Tiny chunks (1-7 BGZF blocks of 1.5 KB) and tiny / zero headroom: every record straddles chunk borders and the
+    oversized-carry path is taken; the packets must not change."""
+    reads, contigs = _sorted_reads(9, 200)
+    path = str(tmp_path / "s.bam")
+    bam_writer.write_bam(path, contigs, reads, block_bytes=1500, extra_unmapped=2)
+    chrom_id = {n: i for i, n in enumerate(sorted(n for n, _ in contigs))}
+    rd0, ref = _read_all(path, chrom_id, 1000)
+    rd1, got = _read_all(path, chrom_id, 61, tune=tune, threads=3)
+    assert rd0.names() == rd1.names()
+    cat = lambda ps, k: np.concatenate([p[k] for p in ps])
+    for k in ("chrom", "ref_start", "ref_end", "flag", "mapq", "query_len", "read_id", "cigar", "seq4"):
+        assert np.array_equal(cat(ref, k), cat(got, k)), k
+    for k in ref[0]["sa"]:
+        assert np.array_equal(np.concatenate([p["sa"][k] for p in ref]), np.concatenate([p["sa"][k] for p in got])), k
+    assert sum(len(p["chrom"]) for p in got) == len(reads)
+    rd0.close(); rd1.close()
 
 
 def test_subset_packet(tmp_path):
