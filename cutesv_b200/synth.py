@@ -644,3 +644,15 @@ def pseudo_fasta_line(contig, length, seed=3, width=60):
     rng = np.random.default_rng(seed)
     alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
     return alphabet[rng.integers(0, 4, length)].tobytes().decode()
+
+
+def random_params(seed):
+    """Flag combinations well away from the presets (every cuteSV clustering / genotyping flag), for parity sweeps."""
+    rng = np.random.default_rng(seed)
+    ms = int(rng.choice([1, 2, 3, 5, 8, 10]))
+    return dict(min_support=ms, min_size=int(rng.choice([1, 30, 50, 200])), max_size=int(rng.choice([-1, 1000, 100000])),
+                bias_del=int(rng.choice([1, 20, 100, 200, 1000])), bias_ins=int(rng.choice([1, 20, 100, 1000])),
+                bias_inv=int(rng.choice([10, 500, 2000])), bias_dup=int(rng.choice([10, 500, 2000])), bias_tra=int(rng.choice([5, 50, 400])),
+                ratio_del=float(rng.choice([0.0, 0.1, 0.3, 0.5, 0.9, 2.0])), ratio_ins=float(rng.choice([0.0, 0.2, 0.3, 0.9, 1.5])),
+                ratio_tra=float(rng.choice([0.1, 0.6, 1.0])), remain_reads_ratio=float(rng.choice([0.3, 0.5, 0.8, 1.0, 1.7])),
+                genotype=int(rng.integers(0, 2)), gt_round=int(rng.choice([1, 5, 50, 500])))   # (gt_bias_ins is the reference's constant 1000, resolveINDEL.py:312)

@@ -21,12 +21,17 @@ from oracle import ref_harness  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 CASES = [("adv%03d" % s, ("adversarial", s)) for s in (0, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144)] + [
-    ("cfg2_s0p002", ("config", 2, 0.002)), ("cfg3_s0p004", ("config", 3, 0.004)), ("cfg5_s0p001", ("config", 5, 0.001))]
+    ("cfg2_s0p002", ("config", 2, 0.002)), ("cfg3_s0p004", ("config", 3, 0.004)), ("cfg5_s0p001", ("config", 5, 0.001))] + [
+    ("sweep%02d" % s, ("sweep", s)) for s in range(12)]   # random flag settings (synth.random_params) x adversarial inputs
 
 
 def make_case(spec):
     if spec[0] == "adversarial":
         return synth.adversarial(spec[1], max_sigs=160)
+    if spec[0] == "sweep":
+        cfg = synth.adversarial(3000 + spec[1], max_sigs=160)
+        cfg["params"] = dict(cfg["params"], **synth.random_params(spec[1]))
+        return cfg
     return synth.make_config(spec[1], spec[2])
 
 

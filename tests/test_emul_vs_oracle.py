@@ -39,3 +39,9 @@ def test_emulator_matches_reference_rows(name):
     res = emul_lib.cluster(case["params"], case["lens"], case["sigs"], case["reads"])
     d = compare.diff_rows(case["rows"], golden_util.to_rows(case, res))
     assert not d, "\n".join(d)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_parameter_sweep(seed):
+    """Random flag settings x adversarial inputs (ties, duplicates, pile-ups, half positions)."""
+    _check(synth.adversarial(3000 + seed), **synth.random_params(seed))
