@@ -218,3 +218,10 @@ def test_lanes_off_same_records(engine):
     finally:
         engine.set_lanes(True)
     assert not compare_records.diff_records(a, b)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_parameter_sweep(engine, seed):
+    """Random flag settings (synth.random_params) x adversarial inputs; the first 12 settings are also pinned against
+    the real reference (tests/golden/sweep*.json)."""
+    _run(engine, synth.adversarial(3000 + seed), **synth.random_params(seed))
