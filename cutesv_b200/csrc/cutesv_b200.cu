@@ -57,7 +57,11 @@ struct DBuf {
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) return e;
         cap = want;
-        if (zero_new) return cudaMemset(p, 0, want);
+        if (zero_new) {   // visible to every (non-blocking) stream before ensure() returns
+            e = cudaMemset(p, 0, want);
+            if (e != cudaSuccess) return e;
+            return cudaDeviceSynchronize();
+        }
         return cudaSuccess;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -575,14 +579,16 @@ static int make_sync(csv_ctx* c, size_t status_words, TileSync* ts) {
 // ------------------------------------------------------------------------------------------
 template <typename K>
 static int radix_sort(csv_ctx* c, K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* vals_b, bool iota, int64_t n,
-                      const uint32_t* n_dev, int bits, K** keys_out, uint32_t** vals_out, int dom_type = -1) {
+                      const uint32_t* n_dev, int bits, K** keys_out, uint32_t** vals_out, int dom_type = -1, bool hist_ready = false) {
     const int passes = std::max(1, (bits + 7) / 8);
     if (passes > RS_MAX_PASSES) return set_err(CSV_E_INVALID, "radix sort: %d bits", bits);
     constexpr int TILE = RS_THREADS * RsTraits<K>::ITEMS;
     const int64_t n_tiles = (n + TILE - 1) / TILE;
     CU(c->hist.ensure(RS_MAX_PASSES * 256 * 4));
-    CU(cudaMemsetAsync(c->hist.p, 0, RS_MAX_PASSES * 256 * 4, c->stream));
-    LAUNCH(c, (k_rs_hist<K>), grid_for(c, n, RS_THREADS * 16, 4), RS_THREADS, 0, keys_a, n, n_dev, passes, c->hist.as<uint32_t>());
+    if (!hist_ready) {   // (the density pre-filter already counted the digits of its survivors)
+        CU(cudaMemsetAsync(c->hist.p, 0, RS_MAX_PASSES * 256 * 4, c->stream));
+        LAUNCH(c, (k_rs_hist<K>), grid_for(c, n, RS_THREADS * 16, 4), RS_THREADS, 0, keys_a, n, n_dev, passes, c->hist.as<uint32_t>());
+    }
     LAUNCH(c, k_rs_hist_scan, 1, 256, 0, c->hist.as<uint32_t>(), passes);
     K* ki = keys_a; K* ko = keys_b;
     uint32_t* vi = vals_a; uint32_t* vo = vals_b;
@@ -696,17 +702,20 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
     const size_t n_bkt = (((size_t)(total >> BKT_SHIFT) + 4096) / 4096 + 1) * 4096 + 3 * BKT_PAD + 64;
     stage_begin(c, CSV_ST_KEYS);
     if (prefilter) {
-        CU(c->bkt.ensure(n_bkt * 4));
-        CU(cudaMemsetAsync(c->bkt.p, 0, n_bkt * 4, c->stream));
+        // the bucket histogram is all-zero between calls: zeroed when (re)allocated, cleared again by k_prefilter
+        CU(c->bkt.ensure(n_bkt * 4, true));
+        CU(c->hist.ensure(RS_MAX_PASSES * 256 * 4));
+        const int passes = std::max(1, (bits + 7) / 8);
         LAUNCH(c, (k_indel_keys<uint32_t, true>), grid_for(c, n, 256), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(),
                s.rid.as<int32_t>(), n, t == CSV_INS ? 1 : 0, ct, c->keys_b.as<uint32_t>(), &ctr->status, c->bkt.as<uint32_t>());
         uint32_t* n_pass = &ctr->n_dom[t];
         const uint32_t n_buckets = (uint32_t)(total >> BKT_SHIFT) + 1;
         CU(c->bkt_flags.ensure(((size_t)n_buckets / 32 + 2) * 4));
         LAUNCH(c, k_bucket_flags, grid_for(c, n_buckets / 16 + 256, 256, 8), 256, 0, c->bkt.as<uint32_t>(), n_buckets, rb, (uint32_t)J.cp.min_support,
-               c->bkt_flags.as<uint32_t>());
+               c->bkt_flags.as<uint32_t>(), c->hist.as<uint32_t>(), RS_MAX_PASSES * 256);
         LAUNCH(c, k_prefilter, grid_for(c, n, 2048, 8), 256, 0, c->keys_b.as<uint32_t>(), n, c->bkt_flags.as<uint32_t>(),
-               c->keys_a.as<uint32_t>(), c->vals_a.as<uint32_t>(), n_pass);
+               c->keys_a.as<uint32_t>(), c->vals_a.as<uint32_t>(), n_pass, c->bkt.as<uint32_t>(), (int64_t)n_bkt, c->hist.as<uint32_t>(),
+               passes);
         J.n_dev = n_pass;
     } else if (!k64)
         LAUNCH(c, (k_indel_keys<uint32_t, false>), grid_for(c, n, 256), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), s.b.as<int32_t>(),
@@ -721,7 +730,7 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
     if (!k64) {
         uint32_t* ko = nullptr;
         rc = radix_sort<uint32_t>(c, c->keys_a.as<uint32_t>(), c->vals_a.as<uint32_t>(), c->keys_b.as<uint32_t>(),
-                                  c->vals_b.as<uint32_t>(), !prefilter, n, J.n_dev, bits, &ko, &sidx, t);
+                                  c->vals_b.as<uint32_t>(), !prefilter, n, J.n_dev, bits, &ko, &sidx, t, prefilter);
         J.keys32 = ko;
     } else {
         uint64_t* ko = nullptr;

@@ -9,6 +9,7 @@
 #pragma once
 #include "core.h"
 #include "devprims.cuh"
+#include "radix.cuh"
 
 namespace csv {
 
@@ -236,7 +237,9 @@ __global__ void __launch_bounds__(256) k_indel_keys(const int32_t* __restrict__ 
 // signatures" (a superset of the +-R window of every signature in the bucket).  The bit map is
 // 1.5 MB for hg19 and stays cache resident for the per-signature test.
 __global__ void __launch_bounds__(256) k_bucket_flags(const uint32_t* __restrict__ bkt, uint32_t n_buckets, int rb, uint32_t need,
-                                                      uint32_t* __restrict__ flags) {
+                                                      uint32_t* __restrict__ flags, uint32_t* __restrict__ hist_to_clear, int hist_words) {
+    if (blockIdx.x == 0)   // the radix digit histograms k_prefilter accumulates into
+        for (int i = threadIdx.x; i < hist_words; i += 256) hist_to_clear[i] = 0u;
     // A CTA stages 4096 buckets (+ halo) in shared memory with coalesced loads; every thread then
     // slides the window sum along its 16 consecutive buckets; lane pairs assemble a 32-bit word.
     constexpr int PER = 16, TILE = 256 * PER;
@@ -267,9 +270,17 @@ __global__ void __launch_bounds__(256) k_bucket_flags(const uint32_t* __restrict
 // original input index).  2048 signatures per CTA iteration, one reservation atomic per iteration.
 __global__ void __launch_bounds__(256) k_prefilter(const uint32_t* __restrict__ keys, int64_t n, const uint32_t* __restrict__ flags,
                                                    uint32_t* __restrict__ out_keys, uint32_t* __restrict__ out_idx,
-                                                   uint32_t* out_count) {
+                                                   uint32_t* out_count, uint32_t* __restrict__ bkt, int64_t n_bkt,
+                                                   uint32_t* __restrict__ hist, int passes) {
     constexpr int ITEMS = 8;
     __shared__ uint32_t s_warp[10];
+    __shared__ uint32_t s_hist[RS_MAX_PASSES * 256];
+    // Two chores ride along: the bucket histogram is cleared for the next call (it was consumed by k_bucket_flags; the
+    // buffer is all-zero between calls), and the survivors' digit histograms of every radix pass are accumulated here
+    // instead of in a separate read of the compacted keys (hist was zeroed by k_bucket_flags).
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_bkt; i += (int64_t)gridDim.x * 256) bkt[i] = 0u;
+    for (int i = threadIdx.x; i < passes * 256; i += 256) s_hist[i] = 0;
+    __syncthreads();
     const int64_t n_tiles = (n + 256 * ITEMS - 1) / (256 * ITEMS);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * 256 * ITEMS;
@@ -294,8 +305,14 @@ __global__ void __launch_bounds__(256) k_prefilter(const uint32_t* __restrict__ 
                 out_keys[o] = key[j];
                 out_idx[o] = (uint32_t)(base + j * 256 + threadIdx.x);
                 o++;
+                for (int p = 0; p < passes; p++) atomicAdd(&s_hist[p * 256 + (int)((key[j] >> (8 * p)) & 0xff)], 1u);
             }
         }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * 256; i += 256) {
+        const uint32_t v = s_hist[i];
+        if (v) atomicAdd(&hist[i], v);
     }
 }
 
