@@ -141,6 +141,8 @@ struct csv_ctx {
     DBuf d_goff[CSV_NTYPES + 1];   // contig row offsets of grouped uploads (last: reads table)
     LaneWork lanes[N_LANES - 1];   // lane 0 = the ctx's own stream and buffers
     cudaEvent_t ev_fork = nullptr;
+    cudaStream_t aux_stream = nullptr;   // resets of the genotype stage's scratch run beside the lanes
+    cudaEvent_t ev_aux = nullptr;
     bool lanes_enabled = true;
     // segment / cluster
     DBuf kept[CSV_NTYPES], big_list, giant_list, giant_arena, cnt;
@@ -295,6 +297,8 @@ extern "C" int csv_create(int device, void* stream, csv_ctx** out) {
         for (int i = 0; i <= CSV_NTYPES && e4 == cudaSuccess; i++) e4 = cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming);
         if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
         if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+        if (e4 == cudaSuccess) e4 = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+        if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming);
         for (int l = 0; l < N_LANES - 1 && e4 == cudaSuccess; l++) {
             e4 = cudaStreamCreateWithFlags(&c->lanes[l].stream, cudaStreamNonBlocking);
             if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->lanes[l].ev_join, cudaEventDisableTiming);
@@ -345,6 +349,8 @@ extern "C" int csv_destroy(csv_ctx* c) {
         for (DBuf* b : lb) b->release();
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
+    if (c->ev_aux) cudaEventDestroy(c->ev_aux);
     for (int i = 0; i <= CSV_NTYPES; i++) c->d_goff[i].release();
     for (int t = 0; t < CSV_NTYPES; t++) {
         c->sig[t].chrom.release(); c->sig[t].a.release(); c->sig[t].b.release(); c->sig[t].rid.release(); c->sig[t].c.release();
@@ -908,6 +914,24 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
     const bool lanes = c->lanes_enabled;
     if (lanes) CU(cudaEventRecord(c->ev_fork, c->stream));
     for (int l = 0; l < N_LANES - 1; l++) c->lanes[l].used = false;
+    // genotype-stage scratch (bin tables of the linear coordinate): sized and cleared now, beside the lanes
+    const uint64_t total_len = c->contig_off[c->n_contigs];
+    int geno_shift = 10;
+    while ((total_len >> geno_shift) > (1u << 20)) geno_shift++;
+    const uint32_t geno_bins = (uint32_t)(total_len >> geno_shift) + 2;
+    bool aux_used = false;
+    if (c->P.genotype) {
+        CU(c->bin_start.ensure(((size_t)geno_bins + 1) * 4));
+        CU(c->bin_fill.ensure((size_t)geno_bins * 4));
+        CU(c->bin_bits.ensure(((size_t)geno_bins / 32 + 2) * 4));
+        cudaStream_t rs = lanes ? c->aux_stream : c->stream;
+        if (lanes) CU(cudaStreamWaitEvent(rs, c->ev_fork, 0));
+        CU(cudaMemsetAsync(c->bin_start.p, 0, ((size_t)geno_bins + 1) * 4, rs));
+        CU(cudaMemsetAsync(c->bin_fill.p, 0, (size_t)geno_bins * 4, rs));
+        CU(cudaMemsetAsync(c->bin_bits.p, 0, ((size_t)geno_bins / 32 + 2) * 4, rs));
+        CU(cudaMemsetAsync(c->has_rows.p, 0, (size_t)c->n_contigs, rs));
+        if (lanes) { CU(cudaEventRecord(c->ev_aux, rs)); aux_used = true; }
+    }
     for (int t = 0; t < CSV_NTYPES; t++) {
         if (!(type_mask >> t & 1) || c->sig[t].n == 0) continue;
         LaneWork* L = (lanes && lane_of(t) > 0) ? &c->lanes[lane_of(t) - 1] : nullptr;
@@ -918,11 +942,16 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
         rc = wait_upload(c, t);
         if (!rc) rc = (t == CSV_DEL || t == CSV_INS) ? run_indel(c, t, kslot_base) : run_other(c, t, kslot_base);
         if (L) lane_swap(c, *L);
-        if (rc) { join_lanes(c); return rc; }   // the ctx stream must not run ahead of work already forked
+        if (rc) {   // the ctx stream must not run ahead of work already forked
+            join_lanes(c);
+            if (aux_used) cudaStreamWaitEvent(c->stream, c->ev_aux, 0);
+            return rc;
+        }
         kslot_base += c->kept_cap[t];
     }
     rc = join_lanes(c);
     if (rc) return rc;
+    if (aux_used) CU(cudaStreamWaitEvent(c->stream, c->ev_aux, 0));
     // ---- order ----
     stage_begin(c, CSV_ST_ORDER);
     {
@@ -942,28 +971,18 @@ extern "C" int csv_cluster(csv_ctx* c, uint32_t type_mask) {
     {
         GenoJob G;
         memset(&G, 0, sizeof(G));
-        const uint64_t total = c->contig_off[c->n_contigs];
-        int shift = 10;
-        while ((total >> shift) > (1u << 20)) shift++;
         G.cand = c->cand.as<csv_cand>(); G.geno = c->geno.as<csv_geno>(); G.names = c->names.as<int32_t>(); G.ctr = ctr;
         G.cap_cand = c->cap_cand;
         G.ct = ContigTab{c->d_off.as<uint64_t>(), c->d_len.as<int64_t>(), c->n_contigs};
         G.gp = GtParams{c->P.bias_del, c->P.gt_bias_ins, c->P.bias_dup, c->P.bias_inv};
-        G.shift = shift;
-        G.n_bins = (uint32_t)(total >> shift) + 2;
-        CU(c->bin_start.ensure(((size_t)G.n_bins + 1) * 4));
-        CU(c->bin_fill.ensure((size_t)G.n_bins * 4));
-        CU(c->bin_bits.ensure(((size_t)G.n_bins / 32 + 2) * 4));
+        G.shift = geno_shift;
+        G.n_bins = geno_bins;
         G.bin_start = c->bin_start.as<uint32_t>(); G.bin_fill = c->bin_fill.as<uint32_t>(); G.bin_bits = c->bin_bits.as<uint32_t>();
         G.win_list = c->win_list.as<uint32_t>(); G.win_cap = c->cap_cand * 2;
         G.dr = c->dr.as<uint32_t>(); G.has_rows = c->has_rows.as<uint8_t>();
         G.gl_table = c->gl_table.as<csv_geno>();
         G.genotype = c->P.genotype;
         if (c->P.genotype) {
-            CU(cudaMemsetAsync(G.bin_start, 0, ((size_t)G.n_bins + 1) * 4, c->stream));
-            CU(cudaMemsetAsync(G.bin_fill, 0, (size_t)G.n_bins * 4, c->stream));
-            CU(cudaMemsetAsync(G.bin_bits, 0, ((size_t)G.n_bins / 32 + 2) * 4, c->stream));
-            CU(cudaMemsetAsync(G.has_rows, 0, (size_t)c->n_contigs, c->stream));
             LAUNCH(c, (k_windows<0>), grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
             TileSync ts;
             rc = make_sync(c, (size_t)((G.n_bins + 1) / SEL_TILE + 2), &ts);
