@@ -321,7 +321,28 @@ def main():
             gbs = nbytes / 1e9 / (ms / 1e3) if ms > 0 else 0.0
             kernels[st] = {"kernel": kname, "ms_per_step": ms, "algorithmic_bytes_per_step": nbytes, "launches_per_step": launches_per_step,
                            "achieved": gbs, "frac": gbs / peak}
+        # dominant KERNEL (the stages lump several kernels: keys = k_indel_keys + k_bucket_flags + k_prefilter, ...):
+        # the one with the largest total time in the committed ncu launch list of this same command
+        # (profiles/r01_launches_final.txt); without the file, the longest stage
         dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        dom_basis = "longest stage by CUDA events"
+        try:
+            tot = {}
+            named = {"k_cluster_warp": "cluster", "k_rs_onesweep": "sort", "k_indel_keys": "keys", "k_reads_pass": "genotype"}
+            for ln in open(os.path.join(ROOT, "profiles", "r01_launches_final.txt")):
+                if "launches=" not in ln:
+                    continue
+                nm = ln.split("launches=")[0]
+                n_l = int(ln.split("launches=")[1].split()[0])
+                avg = float(ln.split("avg=")[1].split()[0])
+                for key, st in named.items():
+                    if key in nm:
+                        tot[st] = tot.get(st, 0.0) + n_l * avg
+            if tot and args.config == 2:
+                dom = max(tot, key=tot.get)
+                dom_basis = "largest kernel total in profiles/r01_launches_final.txt (ncu launch list of this command)"
+        except Exception:
+            pass
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
@@ -353,7 +374,8 @@ def main():
                          "share_of_step": kernels[dom]["ms_per_step"] / max(dev_stage_sum, 1e-9),
                          "timing": "CUDA events around the stage on the ctx stream, K steps with the SV-type lanes serialised "
                                    "(%.4f ms/step; the timed region overlaps the lanes: %.4f ms/step)" % (serial_ms, dev_ms_max / args.steps),
-                         "note": "dominant stage by CUDA-event time; it is latency/instruction bound, not DRAM bound (profiles/)"},
+                         "dominant_by": dom_basis,
+                         "note": "latency / instruction bound, not DRAM bound (profiles/); roofline_kernels lists every stage"},
             "roofline_kernels": kernels,
             "roofline_pipeline": {"algorithmic_bytes_per_step": alg, "achieved": alg / 1e9 / (dev_ms_max / args.steps / 1e3), "unit": "GB/s",
                                   "frac": alg / 1e9 / (dev_ms_max / args.steps / 1e3) / peak},
