@@ -1,7 +1,7 @@
 """Host side of the boundary: decoded alignment records -> pinned-friendly columnar int32 buffers.
 
-BAM decoding itself stays with pysam (north star); this module only packs the fields the
-reference reads at cuteSV:606-733 from duck-typed read objects (.flag .mapq .query_length
+Packs the fields the reference reads at cuteSV:606-733 from duck-typed read objects (pysam records for CRAM / SAM
+input, test doubles; plain BAM goes through the native decoder in bamio.py instead) (.flag .mapq .query_length
 .query_name .reference_start .reference_end .cigartuples .get_tags()).
 """
 import re
