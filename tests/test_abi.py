@@ -54,3 +54,22 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
                 assert "emul_lib" not in txt, f
+
+
+def test_group_by_contig_is_stable_and_complete():
+    """Grouped host inputs (csv_*_grouped): stable regrouping by contig + row offsets."""
+    import numpy as np
+    from cutesv_b200 import _abi, synth
+    cfg = synth.adversarial(5)
+    nc = len(cfg["lens"])
+    for cols in list(cfg["sigs"].values()) + [cfg["reads"]]:
+        g = _abi.group_by_contig(cols, nc)
+        off = g["contig_off"]
+        assert off[0] == 0 and off[-1] == len(cols["chrom"]) and np.all(np.diff(off) >= 0) and "chrom" not in g
+        order = np.argsort(cols["chrom"], kind="stable")
+        for k, v in cols.items():
+            if k == "chrom" or v is None:
+                continue
+            assert np.array_equal(g[k], np.asarray(v)[order]), k
+        for c in range(nc):   # rows of contig c, in their original relative order
+            assert np.all(np.asarray(cols["chrom"])[order][off[c]:off[c + 1]] == c)
