@@ -60,6 +60,17 @@ def materialise_config1(d):
     return bam, fa, os.path.join(d, "c1.vcf"), wd
 
 
+# further flag sets on data set 1 (VCF formatting branches: RNAMES, no genotype / no sequences, size limits, presets)
+EXTRA_FLAG_SETS = {
+    "cli_dataset1_hifi_readid": ["--genotype", "--report_readid", "-s", "3", "-l", "50", "-L", "-1", "--max_cluster_bias_INS", "1000",
+                                 "--diff_ratio_merging_INS", "0.9", "--max_cluster_bias_DEL", "1000", "--diff_ratio_merging_DEL", "0.5",
+                                 "-q", "10", "-r", "1000", "--remain_reads_ratio", "0.8", "--threads", "3", "-S", "SAMPLE7"],
+    "cli_dataset1_nogt_noseq": ["-s", "4", "--ignore_sequence", "-L", "400", "--max_cluster_bias_INS", "100", "--diff_ratio_merging_INS", "0.3",
+                                "--max_cluster_bias_DEL", "100", "--diff_ratio_merging_DEL", "0.3", "--threads", "2", "-b", "30000",
+                                "-md", "500", "-mi", "500", "-sl", "20", "-p", "3"],
+}
+
+
 def main():
     import pysam  # noqa: F401  (the fake one, first on sys.path)
     from oracle import ref_harness
@@ -88,6 +99,15 @@ def main():
     with open(os.path.join(ROOT, "tests", "golden", "cli_dataset1_bed.json"), "w") as f:
         json.dump(dict(flags=FLAGS, lines=lines), f)
     print("dataset1 + include_bed:", len(lines) - 1, "records")
+    for name, flags in EXTRA_FLAG_SETS.items():
+        dx = tempfile.mkdtemp()
+        bam, fa, out, wd = materialise(dx)
+        argv = [bam, fa, out, wd] + flags
+        m["main"].main_ctrl(parseArgs(argv), argv)
+        lines = [l for l in open(out) if not l.startswith("##")]
+        with open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w") as f:
+            json.dump(dict(flags=flags, lines=lines), f)
+        print(name, len(lines) - 1, "records")
 
 
 if __name__ == "__main__":

@@ -54,6 +54,21 @@ def test_cli_native_bam_config1_cpu(tmp_path):
     assert len(lines) > 250 and lines == gold
 
 
+@pytest.mark.parametrize("name", ["cli_dataset1_hifi_readid", "cli_dataset1_nogt_noseq"])
+def test_cli_native_bam_flag_sets_cpu(tmp_path, name):
+    """Other flag sets (RNAMES, no genotype / no sequences, size limits, merge thresholds, max_split_parts):
+    VCF body identical to the reference's own run with the same flags."""
+    from emul_engine import EmulEngine
+    bamio.build()
+    gold = json.load(open(os.path.join(golden_util.GOLDEN, name + ".json")))
+    pk, fa, out, wd = gen_cli_golden.materialise(str(tmp_path))
+    bam = _to_real_bam(pk, str(tmp_path / "real.bam"))
+    argv = [bam, fa, out, wd] + gold["flags"]
+    cli.main_ctrl(cli.build_parser().parse_args(argv), argv, engine=EmulEngine())
+    import vcf_util
+    assert vcf_util.normalise_rnames([l for l in open(out) if not l.startswith("##")]) == vcf_util.normalise_rnames(gold["lines"])
+
+
 def test_cli_native_bam_include_bed_cpu(tmp_path):
     from emul_engine import EmulEngine
     lines, gold, _ = _run(EmulEngine(), tmp_path, 3)

@@ -16,3 +16,16 @@ def rows_by_chrom(rows):
             if tt == t:
                 out.setdefault(chrom, []).extend([list(x) for x in r])
     return out
+
+
+def normalise_rnames(lines):
+    """DUP / BND RNAMES come from Python set iteration in the reference (hash-seed dependent, resolveDUP.py:82,96;
+    resolveTRA.py:182): compare those lists as sets."""
+    out = []
+    for ln in lines:
+        if "RNAMES=" in ln and ("SVTYPE=DUP" in ln or "SVTYPE=BND" in ln):
+            head, rest = ln.split("RNAMES=", 1)
+            names, tail = rest.split(";", 1)
+            ln = head + "RNAMES=" + ",".join(sorted(names.split(","))) + ";" + tail
+        out.append(ln)
+    return out
