@@ -236,12 +236,13 @@ def main_ctrl(args, argv, engine=None):
             if tt == t:
                 results.setdefault(chrom, []).extend(r)
     logging.info("Writing to your output file.")
-    reference = vcf.read_fasta(args.reference)
+    reference = vcf.IndexedFasta(args.reference)   # random access through <ref>.fai (built on the fly when missing)
     opts = dict(genotype=args.genotype, max_size=args.max_size, min_size=args.min_size, report_readid=args.report_readid,
                 ignore_sequence=args.ignore_sequence)
     vcf.write_vcf(args.output, results, reference, contig_info, args.sample, argv, opts)
     if args.retain_work_dir:
         _write_workdir(tmp, sigs, reads_cols, chrom_names, read_names, acc.ins_seq, args.write_old_sigs)
+    reference.close()
     source.close()
     return results
 

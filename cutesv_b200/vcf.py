@@ -4,6 +4,7 @@ Restates generate_output (cuteSV_genotype.py:242-467), the header (cuteSV_Descri
 and the serial SVID numbering (cuteSV:1208-1237).  Pure string formatting + FASTA lookups: it stays on
 the host by design; it consumes exactly the rows the reference's resolution_* return.
 """
+import os
 import time
 
 VERSION = "2.1.4"
@@ -167,6 +168,95 @@ def read_fasta(path):
     if name is not None:
         seqs[name] = "".join(chunks)
     return seqs
+
+
+class _LazySeq(object):
+    """One contig of an indexed FASTA: `seq[i]` / `seq[a:b]` read just those bases (str semantics for the
+    non-negative indices generate_output uses)."""
+
+    def __init__(self, fh, length, offset, line_bases, line_width):
+        self.fh, self.length, self.offset, self.lb, self.lw = fh, length, offset, line_bases, line_width
+
+    def __len__(self):
+        return self.length
+
+    def _read(self, a, b):
+        if b <= a:
+            return ""
+        start = self.offset + (a // self.lb) * self.lw + a % self.lb
+        end = self.offset + ((b - 1) // self.lb) * self.lw + (b - 1) % self.lb + 1
+        self.fh.seek(start)
+        return self.fh.read(end - start).replace(b"\n", b"").replace(b"\r", b"").decode()
+
+    def __getitem__(self, key):
+        if isinstance(key, slice):
+            a, b, step = key.indices(self.length)
+            if step != 1:
+                return self._read(0, self.length)[key]
+            return self._read(a, b)
+        i = key + self.length if key < 0 else key
+        if not 0 <= i < self.length:
+            raise IndexError("string index out of range")
+        return self._read(i, i + 1)
+
+
+class IndexedFasta(object):
+    """dict-like {contig: sequence} over a FASTA without loading it: uses <path>.fai when present, else builds the same
+    index in one pass.  Falls back to read_fasta() for files faidx could not index (ragged line lengths)."""
+
+    def __init__(self, path):
+        self.entries = {}
+        self.full = None
+        fai = path + ".fai"
+        if os.path.exists(fai):
+            with open(fai) as f:
+                for line in f:
+                    c = line.rstrip("\n").split("\t")
+                    if len(c) >= 5:
+                        self.entries[c[0]] = (int(c[1]), int(c[2]), int(c[3]), int(c[4]))
+        else:
+            ok = self._build(path)
+            if not ok:
+                self.full = read_fasta(path)
+        self.fh = open(path, "rb") if self.full is None else None
+
+    def _build(self, path):
+        name, length, offset, lb, lw, short_seen, pos = None, 0, 0, 0, 0, False, 0
+        with open(path, "rb") as f:
+            for line in f:
+                n = len(line)
+                if line.startswith(b">"):
+                    if name is not None:
+                        self.entries[name] = (length, offset, lb or 1, lw or 1)
+                    name, length, offset, lb, lw, short_seen = line[1:].split()[0].decode(), 0, pos + n, 0, 0, False
+                elif name is not None:
+                    bases = len(line.rstrip(b"\r\n"))
+                    if short_seen and bases:
+                        return False              # a full-length line after a shorter one: not indexable
+                    if lb == 0:
+                        lb, lw = bases, n
+                    elif bases != lb or n != lw:
+                        if bases > lb:
+                            return False
+                        short_seen = True
+                    length += bases
+                pos += n
+        if name is not None:
+            self.entries[name] = (length, offset, lb or 1, lw or 1)
+        return True
+
+    def __contains__(self, chrom):
+        return chrom in (self.full if self.full is not None else self.entries)
+
+    def __getitem__(self, chrom):
+        if self.full is not None:
+            return self.full[chrom]
+        return _LazySeq(self.fh, *self.entries[chrom])
+
+    def close(self):
+        if self.fh:
+            self.fh.close()
+            self.fh = None
 
 
 def write_vcf(path, results_by_chrom, reference, contig_info, sample, argv, opts, date=None):

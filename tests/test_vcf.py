@@ -69,3 +69,47 @@ def test_header_matches_reference_when_present():
         if a.startswith("##fileDate"):
             continue
         assert a == b
+
+
+def test_indexed_fasta_equals_full_load(tmp_path):
+    """vcf.IndexedFasta (random access, .fai or on-the-fly index) vs read_fasta on every access pattern format_records uses."""
+    import numpy as np
+    from cutesv_b200 import vcf
+    rng = np.random.default_rng(3)
+    seqs = {"chrA": "".join(rng.choice(list("ACGTN"), 1234)), "chrB": "".join(rng.choice(list("acgtRY"), 60)), "c3": "A", "chrD": "".join(rng.choice(list("ACGT"), 601))}
+    fa = tmp_path / "r.fa"
+    with open(fa, "w") as f:
+        for k, v in seqs.items():
+            f.write(">%s some description\n" % k)
+            for i in range(0, len(v), 60):
+                f.write(v[i:i + 60] + "\n")
+    full = vcf.read_fasta(str(fa))
+    assert full == seqs
+    for use_fai in (False, True):
+        if use_fai:   # a samtools-style index
+            off = 0
+            lines = []
+            data = open(fa, "rb").read()
+            for k, v in seqs.items():
+                off = data.index((">%s some description\n" % k).encode()) + len(">%s some description\n" % k)
+                lines.append("%s\t%d\t%d\t%d\t%d\n" % (k, len(v), off, min(60, len(v)), min(60, len(v)) + 1))
+            open(str(fa) + ".fai", "w").write("".join(lines))
+        idx = vcf.IndexedFasta(str(fa))
+        assert "chrA" in idx and "nope" not in idx
+        for k, v in seqs.items():
+            s = idx[k]
+            assert len(s) == len(v)
+            for _ in range(200):
+                a, b = sorted(int(x) for x in rng.integers(0, len(v) + 5, 2))
+                assert s[a:b] == v[a:b], (k, a, b)
+                i = int(rng.integers(0, len(v)))
+                assert s[i] == v[i]
+            assert s[5:2] == "" and s[len(v):len(v) + 3] == ""
+            with pytest.raises(IndexError):
+                s[len(v)]
+        idx.close()
+    ragged = tmp_path / "ragged.fa"
+    ragged.write_text(">x\nACGT\nAC\nACGTAC\n>y\nTT\n")
+    idx = vcf.IndexedFasta(str(ragged))   # not indexable: falls back to the full load
+    assert idx["x"] == "ACGTACACGTAC" and idx["y"][0:2] == "TT"
+    idx.close()
