@@ -94,3 +94,13 @@ def test_cli_pysam_path_include_bed_cpu(tmp_path, monkeypatch):
 def test_cli_native_bam_gpu(engine, tmp_path, which):
     lines, gold, _ = _run(engine, tmp_path, which)
     assert lines == gold
+
+
+@pytest.mark.parametrize("which,packet", [(2, 700), (1, 97)])
+def test_cli_native_bam_many_packets_cpu(tmp_path, monkeypatch, which, packet):
+    """Small extraction packets (several csv_extract calls, provisional read ids and alignment chunks spanning packets):
+    the VCF body must not depend on the packet size."""
+    from emul_engine import EmulEngine
+    monkeypatch.setattr(cli, "PACKET_READS", packet)
+    lines, gold, _ = _run(EmulEngine(), tmp_path, which)
+    assert lines == gold
