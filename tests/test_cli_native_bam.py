@@ -104,3 +104,18 @@ def test_cli_native_bam_many_packets_cpu(tmp_path, monkeypatch, which, packet):
     monkeypatch.setattr(cli, "PACKET_READS", packet)
     lines, gold, _ = _run(EmulEngine(), tmp_path, which)
     assert lines == gold
+
+
+def test_cli_pysam_path_many_packets_cpu(tmp_path, monkeypatch):
+    """The pysam-shaped source (window-by-window fetch through the test-only fake pysam) with small packets."""
+    import sys
+    from emul_engine import EmulEngine
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "tests", "fake_pysam"))
+    monkeypatch.setattr(cli, "PACKET_READS", 211)
+    sys.modules.pop("pysam", None)
+    gold = json.load(open(os.path.join(golden_util.GOLDEN, "cli_dataset1.json")))
+    bam, fa, out, wd = gen_cli_golden.materialise(str(tmp_path))
+    argv = [bam, fa, out, wd] + gold["flags"]
+    cli.main_ctrl(cli.build_parser().parse_args(argv), argv, engine=EmulEngine())
+    assert [l for l in open(out) if not l.startswith("##")] == gold["lines"]
+    sys.modules.pop("pysam", None)
