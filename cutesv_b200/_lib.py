@@ -49,7 +49,17 @@ _SIGNATURES = {
     "csv_set_profiling": (C.c_int, [_VP, C.c_int]),
     "csv_set_lanes": (C.c_int, [_VP, C.c_int]),
     "csv_stage_ms": (C.c_int, [_VP, C.POINTER(C.c_float)]),
+    "csv_kernel_times": (C.c_int64, [_VP, C.c_char_p, C.c_int64]),
     "csv_launch_count": (C.c_int64, [_VP]),
+    "csv_graph_replays": (C.c_int64, [_VP]),
+    "csv_set_shard": (C.c_int, [_VP, C.POINTER(C.c_uint8)]),
+    "csv_comm_unique_id": (C.c_int, [_VP, C.c_size_t]),
+    "csv_comm_init": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
+    "csv_comm_destroy": (C.c_int, [_VP]),
+    "csv_allgather": (C.c_int, [_VP]),
+    "csv_gathered_counts": (C.c_int, [_VP, _I64P, _I64P]),
+    "csv_fetch_gathered": (C.c_int, [_VP, _VP, _VP, C.c_int64, _I32P, C.c_int64]),
+    "csv_gathered_device_ptrs": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     "csv_debug_counters": (C.c_int, [_VP, C.POINTER(C.c_uint32)]),
     "csv_sort_probe": (C.c_int, [_VP, C.POINTER(C.c_float), _I64P, C.POINTER(C.c_int32)]),
 }

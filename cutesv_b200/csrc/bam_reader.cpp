@@ -151,12 +151,14 @@ struct Reader {
     int n_threads = 4;
     int batch_blocks = 256;              // BGZF blocks per chunk
     size_t headroom = HEADROOM_DEFAULT;
+    // (declared BEFORE the pools: members are destroyed in reverse order, so the workers are joined before the
+    //  blocks / chunk they inflate into are freed)
+    Batch batch[2];              // [inflight] is being inflated while the parser consumes the other's payload
+    int inflight = -1;
     Pool pool;
     ForkJoin parsers;
     std::vector<ThreadOut> touts;
     std::vector<const uint8_t*> rec_ptr;   // start of every record of the packet being built
-    Batch batch[2];              // [inflight] is being inflated while the parser consumes the other's payload
-    int inflight = -1;
     std::string io_err;          // error met while reading ahead (reported when that batch is consumed)
     // header
     std::vector<std::string> ref_name;
@@ -201,6 +203,7 @@ bool read_blocks(Reader& r, Batch& b, int max_blocks) {
         uint8_t tail[8];
         if ((clen > 0 && fread(blk.comp.data(), 1, clen, r.f) != (size_t)clen) || fread(tail, 1, 8, r.f) != 8) { r.io_err = "truncated BGZF block"; return false; }
         blk.isize = tail[4] | (tail[5] << 8) | (tail[6] << 16) | ((uint32_t)tail[7] << 24);
+        if (blk.isize > 65536u) { r.io_err = "BGZF block larger than 64 KiB"; return false; }   // SAM spec 4.1
         blk.ok = true;
         b.blocks.push_back(std::move(blk));
     }
@@ -327,7 +330,7 @@ typedef struct bamr_packet {
 
 const char* bamr_error(void) { return g_err.c_str(); }
 
-int bamr_open(const char* path, int n_threads, void** out) {
+static int bamr_open_impl(const char* path, int n_threads, void** out) {
     Reader* r = new Reader();
     r->f = fopen(path, "rb");
     if (!r->f) { g_err = std::string("cannot open ") + path; delete r; return -1; }
@@ -335,7 +338,11 @@ int bamr_open(const char* path, int n_threads, void** out) {
     r->pool.start(r->n_threads);
     if (r->n_threads > 1) r->parsers.start(r->n_threads);
     g_err.clear();
-    auto fail = [&](const char* msg) { if (g_err.empty()) g_err = msg; fclose(r->f); r->f = nullptr; delete r; return -1; };
+    auto fail = [&](const char* msg) {
+        if (g_err.empty()) g_err = msg;
+        if (r->inflight >= 0) { r->pool.wait(&r->batch[r->inflight]); r->inflight = -1; }   // a read-ahead batch may still be inflating
+        fclose(r->f); r->f = nullptr; delete r; return -1;
+    };
     if (ensure(*r, 12) <= 0 || memcmp(r->cur, "BAM\1", 4) != 0) return fail("not a BAM file");
     const int32_t l_text = rd_i32(r->cur + 4);
     if (l_text < 0 || ensure(*r, 12 + (size_t)l_text) <= 0) return fail("truncated BAM header");
@@ -361,6 +368,7 @@ int bamr_open(const char* path, int n_threads, void** out) {
 void bamr_close(void* h) {
     Reader* r = (Reader*)h;
     if (!r) return;
+    if (r->inflight >= 0) { r->pool.wait(&r->batch[r->inflight]); r->inflight = -1; }   // closing before EOF: drain the read-ahead
     if (r->f) fclose(r->f);
     delete r;
 }
@@ -433,12 +441,14 @@ static void parse_range(Reader& r, size_t lo, size_t hi, ThreadOut& o) {
         const size_t s0 = o.sa_chrom.size();
         if (sa) {  // "rname,pos,strand,CIGAR,mapQ,NM;" ... (cuteSV:489-509)
             const char* s = sa;
-            while (*s) {
+            const char* lim = (const char*)end;   // never past the record, whether or not the NUL is there
+            while (s < lim && *s) {
                 const char* e = s;
-                while (*e && *e != ';') e++;
+                while (e < lim && *e && *e != ';') e++;
+                const bool closed = e < lim && *e == ';';   // the reference keeps split(';')[:-1]: an entry without ';' is dropped (cuteSV:678)
                 const char* f[6]; int nf = 0; f[nf++] = s;
                 for (const char* q = s; q < e && nf < 6; q++) if (*q == ',') f[nf++] = q + 1;
-                if (nf >= 5) {
+                if (closed && nf >= 5) {
                     std::string rn(f[0], (size_t)(f[1] - f[0] - 1));
                     auto ri = r.ref_index.find(rn);
                     int32_t fc, lc, sp;
@@ -449,7 +459,8 @@ static void parse_range(Reader& r, size_t lo, size_t hi, ThreadOut& o) {
                     o.sa_mapq.push_back(atoi(f[4]));
                     o.sa_first.push_back(fc); o.sa_last.push_back(lc); o.sa_span.push_back(sp);
                 }
-                s = *e ? e + 1 : e;
+                s = closed ? e + 1 : e;
+                if (!closed) break;
             }
         }
         r.sa_off[k + 1] = (int64_t)(o.sa_chrom.size() - s0);
@@ -461,7 +472,7 @@ static void parse_range(Reader& r, size_t lo, size_t hi, ThreadOut& o) {
 // -1 on error); pointers stay valid until the next call.
 // Three phases: (1) sequential hop over the block_size chain + read-name ids (first-seen order), (2) the
 // records are parsed by the fork-join pool in contiguous ranges, (3) the variable-length parts are stitched.
-int64_t bamr_next(void* h, int64_t max_records, bamr_packet* out) {
+static int64_t bamr_next_impl(void* h, int64_t max_records, bamr_packet* out) {
     Reader& r = *(Reader*)h;
     r.rec_ptr.clear();
     r.read_id.clear();
@@ -567,7 +578,7 @@ void bamr_decode_seq(const uint8_t* seq4, int64_t l_seq, char* out) {
 
 // Per-reference mapped-read counts from a .bai index (get_index_statistics, cuteSV:1015-1025):
 // the pseudo-bin 37450 of every reference holds (n_mapped, n_unmapped).
-int bamr_index_stats(const char* bai_path, int32_t n_ref, int64_t* mapped) {
+static int bamr_index_stats_impl(const char* bai_path, int32_t n_ref, int64_t* mapped) {
     FILE* f = fopen(bai_path, "rb");
     if (!f) { g_err = std::string("cannot open ") + bai_path; return -1; }
     uint8_t h[8];
@@ -578,11 +589,13 @@ int bamr_index_stats(const char* bai_path, int32_t n_ref, int64_t* mapped) {
         uint8_t b4[4];
         if (fread(b4, 1, 4, f) != 4) break;
         const int32_t n_bin = rd_i32(b4);
+        if (n_bin < 0) { fclose(f); g_err = "malformed BAI (negative bin count)"; return -1; }
         for (int32_t b = 0; b < n_bin; b++) {
             uint8_t bh[8];
             if (fread(bh, 1, 8, f) != 8) { fclose(f); g_err = "truncated BAI"; return -1; }
             const uint32_t bin = rd_u32(bh);
             const int32_t n_chunk = rd_i32(bh + 4);
+            if (n_chunk < 0 || n_chunk > (1 << 26)) { fclose(f); g_err = "malformed BAI (chunk count)"; return -1; }
             std::vector<uint8_t> ch((size_t)n_chunk * 16);
             if (n_chunk && fread(ch.data(), 1, ch.size(), f) != ch.size()) { fclose(f); g_err = "truncated BAI"; return -1; }
             if (bin == 37450 && n_chunk >= 2 && ref < n_ref) { uint64_t m; memcpy(&m, ch.data() + 16, 8); mapped[ref] = (int64_t)m; }
@@ -593,6 +606,17 @@ int bamr_index_stats(const char* bai_path, int32_t n_ref, int64_t* mapped) {
     }
     fclose(f);
     return 0;
+}
+
+// No exception crosses the C boundary (std::bad_alloc on a malformed file, ...): error text in bamr_error().
+int bamr_open(const char* path, int n_threads, void** out) {
+    try { return bamr_open_impl(path, n_threads, out); } catch (const std::exception& e) { g_err = std::string("bamr_open: ") + e.what(); return -1; } catch (...) { g_err = "bamr_open: unknown error"; return -1; }
+}
+int64_t bamr_next(void* h, int64_t max_records, bamr_packet* out) {
+    try { return bamr_next_impl(h, max_records, out); } catch (const std::exception& e) { g_err = std::string("bamr_next: ") + e.what(); return -1; } catch (...) { g_err = "bamr_next: unknown error"; return -1; }
+}
+int bamr_index_stats(const char* bai_path, int32_t n_ref, int64_t* mapped) {
+    try { return bamr_index_stats_impl(bai_path, n_ref, mapped); } catch (const std::exception& e) { g_err = std::string("bamr_index_stats: ") + e.what(); return -1; } catch (...) { g_err = "bamr_index_stats: unknown error"; return -1; }
 }
 
 }  // extern "C"

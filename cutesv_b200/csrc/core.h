@@ -58,7 +58,7 @@ struct CudaTeam {
 // status word bits written by kernels (csv_ctx reports them as CSV_E_INPUT / internal errors)
 enum : uint32_t {
     ST_BAD_CHROM = 1u, ST_BAD_POS = 2u, ST_NEG_FIELD = 4u, ST_POW_TABLE = 8u, ST_CAND_OVERFLOW = 16u,
-    ST_NAMES_OVERFLOW = 32u, ST_LIST_OVERFLOW = 64u, ST_INTERNAL = 128u, ST_UNSORTED = 256u
+    ST_NAMES_OVERFLOW = 32u, ST_LIST_OVERFLOW = 64u, ST_INTERNAL = 128u, ST_UNSORTED = 256u, ST_BIG_RUN = 512u
 };
 
 // counters block in device memory (one per csv_cluster call)
@@ -482,10 +482,15 @@ static constexpr int GL_TABLE_N = 10203;
 // ------------------------------------------------------------------------------------------
 // INDEL: raw (unsorted) columns + the permutation produced by the radix sort of the linearised
 // position; members of a chain cluster are sidx[s .. s+m).
+struct alignas(16) IndelRec { int32_t a, b, rid; uint32_t idx; };   // one 16 B record per signature of the sorted domain
 struct IndelView {
     const int32_t *chrom, *a, *b, *rid, *c;
     const uint32_t* sidx;
     int is_ins;
+    // record mode (rec != nullptr): member j of the sorted domain is rec[j] (+ recc[j] = column c of INS); the
+    // columns above are then only used for the contig of a cluster.  Otherwise members are gathered through sidx.
+    const IndelRec* rec;
+    const int32_t* recc;
 };
 // DUP / INV / TRA: columns already in the reference's full sort order with exact duplicates
 // removed (cuteSV:783-802, 958-969); oidx = original input index.
@@ -558,14 +563,21 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
     for (int j = t; j < M; j += Team::SIZE) {
         K128 k;
         if (j < m) {
-            uint32_t i = in.sidx[s + j];
-            int32_t a = in.a[i];
+            uint32_t i;
+            int32_t a, bb, rr, aux;
+            if (in.rec) {   // one 16 B record (+ 4 B) per member, consecutive in the sorted domain
+                const IndelRec r = in.rec[s + j];
+                i = r.idx; a = r.a; bb = r.b; rr = r.rid; aux = in.recc ? in.recc[s + j] : 0;
+            } else {
+                i = in.sidx[s + j];
+                a = in.a[i]; bb = in.b[i]; rr = in.rid[i]; aux = in.c ? in.c[i] : 0;
+            }
             int32_t pos = in.is_ins ? (a >> 1) : a;
             ar_a[j] = a;
-            ar_aux[j] = in.c ? in.c[i] : 0;
+            ar_aux[j] = aux;
             ar_idx[j] = (int32_t)i;
-            k.hi = pack64(ord32(in.rid[i]), (uint32_t)pos);
-            k.lo = pack64(ord32(in.b[i]), i);   // ties: original input index (independent of arrival order)
+            k.hi = pack64(ord32(rr), (uint32_t)pos);
+            k.lo = pack64(ord32(bb), i);   // ties: original input index (independent of arrival order)
         } else {
             k.hi = ~0ull; k.lo = ~0ull;
         }
@@ -786,7 +798,7 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
             for (int i = t; i < n; i += Team::SIZE) E.names[noff + i] = D_rid[V3[st + i]];
             if (t == 0) {
                 csv_cand c;
-                c.svtype = svtype; c.chrom = in.chrom[in.sidx[s]]; c.pos = pos_out;
+                c.svtype = svtype; c.chrom = in.chrom[in.rec ? in.rec[s].idx : in.sidx[s]]; c.pos = pos_out;
                 c.len = svtype == CSV_DEL ? (int32_t)(-signalLen) : (int32_t)signalLen;
                 c.support = n; c.cipos = cipos; c.cilen = cilen; c.search_pos = search; c.pos2 = 0; c.aux = aux;
                 c.names_off = (int32_t)noff; c.names_cnt = n; c.cluster = (int32_t)kslot; c.flags = 0;

@@ -112,10 +112,15 @@ static constexpr int SEL_ITEMS = 8;
 static constexpr int SEL_TILE = SEL_THREADS * SEL_ITEMS;
 
 struct TileSync {
-    uint32_t* ticket;    // 1 word, zero at launch
-    uint64_t* status;    // >= n_tiles words, never cleared (generation-tagged)
-    uint32_t gen;        // unique per launch
+    uint32_t* ticket;        // 1 word, zero at launch
+    uint64_t* status;        // >= n_tiles words, never cleared (generation-tagged)
+    const uint32_t* epoch;   // device counter, bumped once per csv_cluster call (so that a captured CUDA graph of the
+                             // call can be replayed: the generation is not a frozen kernel argument)
+    uint32_t ordinal;        // unique per look-back launch inside one call (< LB_ORDINALS)
 };
+static constexpr uint32_t LB_ORDINALS = 1024;
+__global__ void k_epoch_bump(uint32_t* epoch) { if (threadIdx.x == 0) *epoch += 1u; }
+__device__ __forceinline__ uint32_t ts_gen(const TileSync& ts) { return (*ts.epoch) * LB_ORDINALS + ts.ordinal; }
 
 // Ordered select: out[k] = i for the k-th i in [0, n) with pred(i); *out_count = number selected.
 // Overflowing out_cap sets `overflow_bit` in *status_word (and keeps counting).
@@ -126,6 +131,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(Pred pred, int64_t n_hos
     __shared__ uint32_t s_warp[9];
     __shared__ uint32_t s_tile, s_excl;
     const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+    const uint32_t gen = ts_gen(ts);
     while (true) {
         if (threadIdx.x == 0) s_tile = atomicAdd(ts.ticket, 1u);
         __syncthreads();
@@ -142,7 +148,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(Pred pred, int64_t n_hos
         uint32_t total;
         const uint32_t local = block_excl_scan_256(cnt, s_warp, &total);
         if (threadIdx.x < 32) {
-            const uint32_t ex = lookback_exclusive_warp(ts.status, ts.gen, (int)tile, total);
+            const uint32_t ex = lookback_exclusive_warp(ts.status, gen, (int)tile, total);
             if (threadIdx.x == 0) {
                 s_excl = ex;
                 if (base + SEL_TILE >= n) *out_count = ex + total;
@@ -162,38 +168,49 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(Pred pred, int64_t n_hos
     }
 }
 
-// In-place exclusive scan of arr[0..n); *total_out (nullable) receives the sum.
-__global__ void __launch_bounds__(SEL_THREADS) k_scan_excl(uint32_t* arr, int64_t n_host, const uint32_t* n_dev,
+// In-place exclusive scan of arr[0..n) (+ *carry_in when given); *total_out (nullable) receives carry + sum.
+// ITEMS consecutive elements per thread: a tile is 256 * ITEMS elements, so large arrays take few tiles and the
+// look-back chain (whose start-up costs one L2 round trip per 32 concurrently running tiles) stays short.
+template <int ITEMS>
+__global__ void __launch_bounds__(SEL_THREADS) k_scan_excl(uint32_t* arr, int64_t n_host, const uint32_t* n_dev, const uint32_t* carry_in,
                                                            uint32_t* total_out, TileSync ts) {
+    constexpr int TILE = SEL_THREADS * ITEMS;
     __shared__ uint32_t s_warp[9];
     __shared__ uint32_t s_tile, s_excl;
-    const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+    int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+    if (n > n_host) n = n_host;
+    const uint32_t carry = carry_in ? *carry_in : 0u;
+    const uint32_t gen = ts_gen(ts);
+    if (n <= 0) {
+        if (total_out && blockIdx.x == 0 && threadIdx.x == 0) *total_out = carry;
+        return;
+    }
     while (true) {
         if (threadIdx.x == 0) s_tile = atomicAdd(ts.ticket, 1u);
         __syncthreads();
         const uint32_t tile = s_tile;
-        const int64_t base = (int64_t)tile * SEL_TILE;
+        const int64_t base = (int64_t)tile * TILE;
         if (base >= n) break;
-        const int64_t i0 = base + (int64_t)threadIdx.x * SEL_ITEMS;
-        uint32_t v[SEL_ITEMS], cnt = 0;
+        const int64_t i0 = base + (int64_t)threadIdx.x * ITEMS;
+        uint32_t v[ITEMS], cnt = 0;
 #pragma unroll
-        for (int j = 0; j < SEL_ITEMS; j++) {
+        for (int j = 0; j < ITEMS; j++) {
             v[j] = (i0 + j < n) ? arr[i0 + j] : 0u;
             cnt += v[j];
         }
         uint32_t total;
         const uint32_t local = block_excl_scan_256(cnt, s_warp, &total);
         if (threadIdx.x < 32) {
-            const uint32_t ex = lookback_exclusive_warp(ts.status, ts.gen, (int)tile, total);
+            const uint32_t ex = lookback_exclusive_warp(ts.status, gen, (int)tile, total);
             if (threadIdx.x == 0) {
                 s_excl = ex;
-                if (total_out && base + SEL_TILE >= n) *total_out = ex + total;
+                if (total_out && base + TILE >= n) *total_out = carry + ex + total;
             }
         }
         __syncthreads();
-        uint32_t run = s_excl + local;
+        uint32_t run = carry + s_excl + local;
 #pragma unroll
-        for (int j = 0; j < SEL_ITEMS; j++) {
+        for (int j = 0; j < ITEMS; j++) {
             if (i0 + j < n) arr[i0 + j] = run;
             run += v[j];
         }

@@ -1,0 +1,295 @@
+// gather_api.inl -- multi-GPU: one csv_ctx per GPU (one process per GPU), contigs sharded over the ranks
+// (csv_set_shard), no data-path collective, ONE NCCL all-gather of the final records (the unit of
+// independence is (svtype, contig): cuteSV:1116-1189).  Included by cutesv_b200.cu.
+//
+// NCCL is resolved with dlopen at first use, so the library still loads on a box without NCCL (the ABI test) and a
+// process that already carries a libnccl (torch) shares that copy.
+
+struct NcclApi {
+    void* h = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool tried = false;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    NcclApi& a = g_nccl;
+    if (a.h) return CSV_OK;
+    if (a.tried) return set_err(CSV_E_STATE, "NCCL is not available (libnccl.so.2 could not be loaded)");
+    a.tried = true;
+    const char* names[] = {getenv("CUTESV_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        if (!nm || !*nm) continue;
+        a.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (a.h) break;
+    }
+    if (!a.h) return set_err(CSV_E_STATE, "NCCL is not available: %s", dlerror());
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
+    a.AllGather = (decltype(a.AllGather))dlsym(a.h, "ncclAllGather");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(a.h, "ncclAllReduce");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.AllReduce || !a.GetErrorString) {
+        a.h = nullptr;
+        return set_err(CSV_E_STATE, "NCCL is not available: symbols missing in libnccl");
+    }
+    return CSV_OK;
+}
+#define NC(call)                                                                                                   \
+    do {                                                                                                           \
+        ncclResult_t r__ = (call);                                                                                 \
+        if (r__ != ncclSuccess) return set_err(CSV_E_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r__));    \
+    } while (0)
+
+static void comm_destroy(csv_ctx* c) {
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    c->comm = nullptr;
+}
+
+extern "C" int csv_comm_unique_id(void* id, size_t bytes) {
+    if (!id || bytes < sizeof(ncclUniqueId)) return set_err(CSV_E_INVALID, "unique id buffer must hold %zu bytes", sizeof(ncclUniqueId));
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId u;
+    NC(g_nccl.GetUniqueId(&u));
+    memset(id, 0, bytes);
+    memcpy(id, &u, sizeof(u));
+    return CSV_OK;
+}
+
+extern "C" int csv_comm_init(csv_ctx* c, const void* id, int rank, int world) {
+    if (!c || !id || world < 1 || rank < 0 || rank >= world) return set_err(CSV_E_INVALID, "bad argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    comm_destroy(c);
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    NC(g_nccl.CommInitRank(&c->comm, world, u, rank));
+    c->rank = rank; c->world = world;
+    c->pad_cand = c->pad_names = 0;
+    if (!c->h_gather) CU(cudaMallocHost((void**)&c->h_gather, 4 * sizeof(int64_t) * 1024));
+    return CSV_OK;
+}
+
+extern "C" int csv_comm_destroy(csv_ctx* c) {
+    if (!c) return set_err(CSV_E_INVALID, "null ctx");
+    comm_destroy(c);
+    c->world = 1; c->rank = 0;
+    return CSV_OK;
+}
+
+// ---- message of one rank: header | pad_cand x csv_cand | pad_cand x csv_geno | pad_names x int32 ----
+static constexpr int64_t GH_WORDS = 4;   // header: n_cand, n_names, overflow, rank (int64 each)
+struct GatherLayout {
+    int64_t pad_cand, pad_names, off_geno, off_names, msg_bytes;
+};
+static GatherLayout gather_layout(int64_t pad_cand, int64_t pad_names) {
+    GatherLayout L;
+    L.pad_cand = pad_cand; L.pad_names = pad_names;
+    L.off_geno = GH_WORDS * 8 + pad_cand * (int64_t)sizeof(csv_cand);
+    L.off_names = L.off_geno + pad_cand * (int64_t)sizeof(csv_geno);
+    L.msg_bytes = (L.off_names + pad_names * 4 + 15) / 16 * 16;
+    return L;
+}
+
+// 16 B words: csv_cand = 4, csv_geno = 2.5 (copied as 8 B words: 5)
+__global__ void __launch_bounds__(256) k_gather_pack(const csv_cand* __restrict__ cand, const csv_geno* __restrict__ geno,
+                                                     const int32_t* __restrict__ names, const Counters* ctr, uint32_t cap_cand,
+                                                     uint32_t cap_names, GatherLayout L, int rank, char* __restrict__ msg) {
+    const int64_t nc = min(ctr->n_cand, cap_cand), nn = min(ctr->n_names, cap_names);
+    const int64_t cc = nc < L.pad_cand ? nc : L.pad_cand, cn = nn < L.pad_names ? nn : L.pad_names;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if (tid == 0) {
+        int64_t* h = (int64_t*)msg;
+        h[0] = nc; h[1] = nn; h[2] = (nc > L.pad_cand || nn > L.pad_names) ? 1 : 0; h[3] = rank;
+    }
+    const uint4* src_c = (const uint4*)cand;
+    uint4* dst_c = (uint4*)(msg + GH_WORDS * 8);
+    for (int64_t i = tid; i < cc * 4; i += stride) dst_c[i] = src_c[i];
+    const uint2* src_g = (const uint2*)geno;
+    uint2* dst_g = (uint2*)(msg + L.off_geno);
+    for (int64_t i = tid; i < cc * 5; i += stride) dst_g[i] = src_g[i];
+    int32_t* dst_n = (int32_t*)(msg + L.off_names);
+    for (int64_t i = tid; i < cn; i += stride) dst_n[i] = names[i];
+}
+
+// Merged order = the single-GPU order: svtype, contig id, then (rank, emission order).  With contig shards every
+// (svtype, contig) group comes from one rank; the (key, rank) counters make the merge well defined for any inputs.
+struct MergeJob {
+    const char* recv; GatherLayout L; int world; int32_t n_contigs;
+    uint32_t* cnt;     // [n_keys * world] counts, then exclusive offsets
+    uint32_t* first;   // [n_keys * world] index (inside its rank) of the first record of the group
+    csv_cand* out_c; csv_geno* out_g; int32_t* out_n; int64_t cap_c, cap_n; uint32_t* status;
+};
+__device__ __forceinline__ const int64_t* gm_header(const MergeJob& M, int r) { return (const int64_t*)(M.recv + (int64_t)r * M.L.msg_bytes); }
+__device__ __forceinline__ int64_t gm_valid(const MergeJob& M, int r) {
+    const int64_t n = gm_header(M, r)[0];
+    return n < M.L.pad_cand ? n : M.L.pad_cand;
+}
+__global__ void __launch_bounds__(256) k_gm_count(MergeJob M) {
+    const int64_t per = M.L.pad_cand, total = per * M.world;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(g / per);
+        const int64_t i = g - (int64_t)r * per;
+        if (i >= gm_valid(M, r)) continue;
+        const csv_cand* cs = (const csv_cand*)(M.recv + (int64_t)r * M.L.msg_bytes + GH_WORDS * 8);
+        const int32_t sv = cs[i].svtype, ch = cs[i].chrom;
+        if (sv < 0 || sv >= CSV_NTYPES || ch < 0 || ch >= M.n_contigs) { atomicOr(M.status, 1u); continue; }
+        const int64_t slot = ((int64_t)sv * M.n_contigs + ch) * M.world + r;
+        if (i == 0 || cs[i - 1].svtype != sv || cs[i - 1].chrom != ch) M.first[slot] = (uint32_t)i;
+        atomicAdd(&M.cnt[slot], 1u);
+    }
+}
+__global__ void __launch_bounds__(256) k_gm_place(MergeJob M) {
+    const int64_t per = M.L.pad_cand, total = per * M.world;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(g / per);
+        const int64_t i = g - (int64_t)r * per;
+        if (i >= gm_valid(M, r)) continue;
+        const char* msg = M.recv + (int64_t)r * M.L.msg_bytes;
+        const csv_cand* cs = (const csv_cand*)(msg + GH_WORDS * 8);
+        csv_cand c = cs[i];
+        if (c.svtype < 0 || c.svtype >= CSV_NTYPES || c.chrom < 0 || c.chrom >= M.n_contigs) continue;
+        const int64_t slot = ((int64_t)c.svtype * M.n_contigs + c.chrom) * M.world + r;
+        const int64_t dst = (int64_t)M.cnt[slot] + (i - (int64_t)M.first[slot]);
+        int64_t nbase = 0;
+        for (int q = 0; q < r; q++) nbase += gm_header(M, q)[1];
+        c.names_off += (int32_t)nbase;
+        c.reserved[1] = r;   // source rank: csv_cand.aux of an INS row indexes THAT rank's INS signature array
+        if (dst < M.cap_c) { M.out_c[dst] = c; M.out_g[dst] = ((const csv_geno*)(msg + M.L.off_geno))[i]; }
+        else atomicOr(M.status, 2u);
+    }
+}
+__global__ void __launch_bounds__(256) k_gm_names(MergeJob M) {
+    int64_t nbase = 0;
+    for (int r = 0; r < M.world; r++) {
+        const int64_t nn = gm_header(M, r)[1];
+        const int64_t cn = nn < M.L.pad_names ? nn : M.L.pad_names;
+        const int32_t* src = (const int32_t*)(M.recv + (int64_t)r * M.L.msg_bytes + M.L.off_names);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cn; i += (int64_t)gridDim.x * blockDim.x)
+            if (nbase + i < M.cap_n) M.out_n[nbase + i] = src[i];
+        nbase += nn;
+    }
+}
+
+static int gather_enqueue(csv_ctx* c) {
+    const GatherLayout L = gather_layout(c->pad_cand, c->pad_names);
+    const int W = c->world;
+    CU(c->g_send.ensure((size_t)L.msg_bytes));
+    CU(c->g_recv.ensure((size_t)L.msg_bytes * W));
+    const int64_t n_keys = (int64_t)CSV_NTYPES * c->n_contigs * W;
+    CU(c->g_scratch.ensure((size_t)n_keys * 8 + 64));
+    CU(c->g_cand.ensure((size_t)L.pad_cand * W * sizeof(csv_cand) + 64));
+    CU(c->g_geno.ensure((size_t)L.pad_cand * W * sizeof(csv_geno) + 64));
+    CU(c->g_names.ensure((size_t)L.pad_names * W * 4 + 64));
+    LAUNCH(c, k_gather_pack, c->n_sm * 2, 256, 0, c->cand.as<csv_cand>(), c->geno.as<csv_geno>(), c->names.as<int32_t>(),
+           c->counters.as<Counters>(), c->cap_cand, c->cap_names, L, c->rank, c->g_send.as<char>());
+    NC(g_nccl.AllGather(c->g_send.p, c->g_recv.p, (size_t)L.msg_bytes, ncclUint8, c->comm, c->stream));
+    CU(cudaMemsetAsync(c->g_scratch.p, 0, (size_t)n_keys * 8 + 64, c->stream));
+    MergeJob M;
+    M.recv = c->g_recv.as<char>(); M.L = L; M.world = W; M.n_contigs = c->n_contigs;
+    M.cnt = c->g_scratch.as<uint32_t>(); M.first = M.cnt + n_keys; M.status = M.first + n_keys;
+    M.out_c = c->g_cand.as<csv_cand>(); M.out_g = c->g_geno.as<csv_geno>(); M.out_n = c->g_names.as<int32_t>();
+    M.cap_c = L.pad_cand * W; M.cap_n = L.pad_names * W;
+    const int grid = grid_for(c, L.pad_cand * W, 256, 4);
+    LAUNCH(c, k_gm_count, grid, 256, 0, M);
+    LAUNCH(c, k_scan_small, 1, 1024, 0, M.cnt, n_keys, (uint32_t*)nullptr);
+    LAUNCH(c, k_gm_place, grid, 256, 0, M);
+    LAUNCH(c, k_gm_names, grid_for(c, L.pad_names, 256, 2), 256, 0, M);
+    // headers of all ranks (+ the merge status word) for csv_gathered_counts
+    for (int r = 0; r < W; r++)
+        CU(cudaMemcpyAsync(c->h_gather + 4 * r, c->g_recv.as<char>() + (size_t)r * L.msg_bytes, GH_WORDS * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_gather + 4 * W, M.status, 4, cudaMemcpyDeviceToHost, c->stream));
+    c->gathered = true;
+    return CSV_OK;
+}
+
+extern "C" int csv_allgather(csv_ctx* c) {
+    if (!c) return set_err(CSV_E_INVALID, "null ctx");
+    if (!c->comm) return set_err(CSV_E_STATE, "csv_comm_init has not been called");
+    if (!c->ran) return set_err(CSV_E_STATE, "csv_cluster has not been called");
+    if (c->world > 1023) return set_err(CSV_E_INVALID, "world size");
+    CU(cudaSetDevice(c->device));
+    if (c->pad_cand == 0 && getenv("CUTESV_B200_GATHER_PAD")) {   // tests: start from a padding that is too small
+        c->pad_cand = std::max<int64_t>(1, atoll(getenv("CUTESV_B200_GATHER_PAD")));
+        c->pad_names = c->pad_cand;
+    }
+    if (c->pad_cand == 0) {
+        // first call: agree on the padded message size (max over ranks, with head room); later calls reuse it and
+        // carry their true counts in the header, so the steady state is pack -> ONE ncclAllGather -> merge, no host sync
+        int64_t nc = 0, nn = 0;
+        int rc = csv_result_counts(c, &nc, &nn);
+        if (rc) return rc;
+        CU(c->g_scratch.ensure(64));
+        int64_t h[2] = {nc, nn};
+        CU(cudaMemcpyAsync(c->g_scratch.p, h, 16, cudaMemcpyHostToDevice, c->stream));
+        NC(g_nccl.AllReduce(c->g_scratch.p, c->g_scratch.p, 2, ncclInt64, ncclMax, c->comm, c->stream));
+        CU(cudaMemcpyAsync(h, c->g_scratch.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->pad_cand = h[0] + h[0] / 4 + 64;
+        c->pad_names = h[1] + h[1] / 4 + 1024;
+    }
+    return gather_enqueue(c);
+}
+
+extern "C" int csv_gathered_counts(csv_ctx* c, int64_t* n_cand, int64_t* n_names) {
+    if (!c) return set_err(CSV_E_INVALID, "null ctx");
+    if (!c->gathered) return set_err(CSV_E_STATE, "csv_allgather has not been called");
+    CU(cudaSetDevice(c->device));
+    for (int attempt = 0; attempt < 4; attempt++) {
+        // the local result must be valid too (input validation, table growth)
+        int rc = finish(c);
+        if (rc == 1) return set_err(CSV_E_STATE, "csv_allgather: the local result needs a rerun (call csv_result_counts before csv_allgather)");
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(c->stream));
+        bool over = false;
+        int64_t tc = 0, tn = 0, mc = 0, mn = 0;
+        for (int r = 0; r < c->world; r++) {
+            const int64_t* h = c->h_gather + 4 * r;
+            over |= h[2] != 0;
+            tc += h[0]; tn += h[1];
+            mc = std::max(mc, h[0]); mn = std::max(mn, h[1]);
+        }
+        if (!over) {
+            if ((uint32_t)c->h_gather[4 * c->world] != 0) return set_err(CSV_E_CUDA, "csv_allgather: merge failed (status %u)", (uint32_t)c->h_gather[4 * c->world]);
+            c->g_n_cand = tc; c->g_n_names = tn;
+            if (n_cand) *n_cand = tc;
+            if (n_names) *n_names = tn;
+            return CSV_OK;
+        }
+        // some rank outgrew the padding: every rank sees the same headers, so every rank repeats with the same new size
+        c->pad_cand = mc + mc / 4 + 64;
+        c->pad_names = mn + mn / 4 + 1024;
+        rc = gather_enqueue(c);
+        if (rc) return rc;
+    }
+    return set_err(CSV_E_CUDA, "csv_allgather: message size did not converge");
+}
+
+extern "C" int csv_fetch_gathered(csv_ctx* c, csv_cand* cands, csv_geno* genos, int64_t cap_cand, int32_t* names, int64_t cap_names) {
+    int64_t nc = 0, nn = 0;
+    int rc = csv_gathered_counts(c, &nc, &nn);
+    if (rc) return rc;
+    if (nc > cap_cand || nn > cap_names) return set_err(CSV_E_CAPACITY, "need %lld candidates / %lld names", (long long)nc, (long long)nn);
+    if (nc) {
+        CU(cudaMemcpyAsync(cands, c->g_cand.p, (size_t)nc * sizeof(csv_cand), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(genos, c->g_geno.p, (size_t)nc * sizeof(csv_geno), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (nn) CU(cudaMemcpyAsync(names, c->g_names.p, (size_t)nn * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return CSV_OK;
+}
+
+extern "C" int csv_gathered_device_ptrs(csv_ctx* c, const csv_cand** cands, const csv_geno** genos, const int32_t** names) {
+    if (!c || !c->gathered) return set_err(CSV_E_STATE, "no gathered results");
+    if (cands) *cands = c->g_cand.as<csv_cand>();
+    if (genos) *genos = c->g_geno.as<csv_geno>();
+    if (names) *names = c->g_names.as<int32_t>();
+    return CSV_OK;
+}

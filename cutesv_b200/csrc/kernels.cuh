@@ -78,13 +78,25 @@ struct HeadPred {
 // "i starts a cluster of >= min_support members" is then a bit test: link[i] == 0 and
 // link[i+1 .. i+min_support-1] all 1.  Ordered compaction as in k_select.
 static constexpr int HEAD_MAX_NEED_WORDS = 64;  // supports min_support up to ~2000 via the mask; above -> generic path
+// INS / DEL record mode (MR.rec != nullptr): the warps of the CTA then walk the kept clusters whose head lies in the
+// tile and gather ONE 16 B record (+ column c of INS) per member through the input index, written at the member's
+// sorted position -- the cluster kernels read a cluster's members as one contiguous range instead of gathering four
+// or five columns per member.  Only members of kept clusters are touched (a fifth of the filter's survivors on 30x ONT).
+struct MemberRec {
+    IndelRec* rec; int32_t* recc;
+    const int32_t *a, *b, *rid, *c;
+    const uint32_t* sidx;
+};
 __global__ void __launch_bounds__(SEL_THREADS) k_select_heads(TypeJob J, uint32_t* out, uint32_t out_cap, uint32_t* out_count,
-                                                              TileSync ts, uint32_t* status_word, uint32_t overflow_bit) {
+                                                              TileSync ts, uint32_t* status_word, uint32_t overflow_bit, MemberRec MR) {
     constexpr int WORDS = SEL_TILE / 32;
     __shared__ uint32_t s_link[WORDS + HEAD_MAX_NEED_WORDS + 2];
     __shared__ uint32_t s_warp[9];
     __shared__ uint32_t s_tile, s_excl;
+    __shared__ uint32_t s_nheads;
+    __shared__ uint16_t s_heads[SEL_TILE];
     const int64_t n = job_n(J);
+    const uint32_t gen = ts_gen(ts);
     const int need = J.cp.min_support;
     const int halo_words = (need + 31) / 32 + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -134,7 +146,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_heads(TypeJob J, uint32_
         uint32_t total;
         const uint32_t local = block_excl_scan_256(cnt, s_warp, &total);
         if (threadIdx.x < 32) {
-            const uint32_t ex = lookback_exclusive_warp(ts.status, ts.gen, (int)tile, total);
+            const uint32_t ex = lookback_exclusive_warp(ts.status, gen, (int)tile, total);
             if (threadIdx.x == 0) {
                 s_excl = ex;
                 if (base + SEL_TILE >= n) *out_count = ex + total;
@@ -147,8 +159,47 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_heads(TypeJob J, uint32_
             if (flags >> j & 1u) {
                 if (o < out_cap) out[o] = (uint32_t)(base + p0 + j);
                 else atomicOr(status_word, overflow_bit);
+                if (MR.rec) s_heads[local + (o - (s_excl + local))] = (uint16_t)(p0 + j);
                 o++;
             }
+        }
+        if (MR.rec) {
+            if (threadIdx.x == 0) s_nheads = total;
+            __syncthreads();
+            const uint32_t nh = s_nheads;
+            uint32_t bad = 0;
+            for (uint32_t h = warp; h < nh; h += SEL_THREADS / 32) {
+                const int64_t s0 = base + s_heads[h];
+                // members s0 .. s0+m-1: 32 links per step until the first missing one
+                int64_t done = 1;
+                while (true) {
+                    const int64_t i = s0 + done + lane;
+                    const bool brk = (i >= n) || !job_linked(J, i);
+                    const uint32_t bm = __ballot_sync(0xffffffffu, brk);
+                    const int take = bm ? __ffs(bm) - 1 : 32;
+                    if (lane < take) {   // element i is a member
+                        const uint32_t x = MR.sidx[i];
+                        IndelRec r;
+                        r.a = MR.a[x]; r.b = MR.b[x]; r.rid = MR.rid[x]; r.idx = x;
+                        const int32_t c5 = MR.c ? MR.c[x] : 0;
+                        if (r.rid < 0 || r.b < 0 || c5 < 0) bad |= ST_NEG_FIELD;
+                        *reinterpret_cast<int4*>(&MR.rec[i]) = *reinterpret_cast<const int4*>(&r);
+                        if (MR.recc) MR.recc[i] = c5;
+                    }
+                    if (bm) break;
+                    done += 32;
+                }
+                if (lane == 0) {   // the head itself
+                    const uint32_t x = MR.sidx[s0];
+                    IndelRec r;
+                    r.a = MR.a[x]; r.b = MR.b[x]; r.rid = MR.rid[x]; r.idx = x;
+                    const int32_t c5 = MR.c ? MR.c[x] : 0;
+                    if (r.rid < 0 || r.b < 0 || c5 < 0) bad |= ST_NEG_FIELD;
+                    *reinterpret_cast<int4*>(&MR.rec[s0]) = *reinterpret_cast<const int4*>(&r);
+                    if (MR.recc) MR.recc[s0] = c5;
+                }
+            }
+            if (bad) atomicOr(status_word, bad);
         }
         __syncthreads();
     }
@@ -316,6 +367,271 @@ __global__ void __launch_bounds__(256) k_prefilter(const uint32_t* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// INS / DEL front end, filter-first: "density filter -> bucket counting sort -> in-bucket order -> member records"
+// (replaces: keys pass + compaction + four stable radix passes over (key, index) + the member gathers of the
+//  cluster kernels).  The bucket histogram the filter needs anyway IS a counting-sort histogram: a prefix sum over
+//  the counts of the flagged buckets gives every flagged bucket its slot range, so ONE scatter pass puts every
+//  survivor into bucket order and a tile-local pass orders the few signatures inside each 256-bp bucket.  The order
+//  among equal keys is irrelevant: every later tie-break uses the input index.
+//  What bounds these kernels on B200 is not DRAM bytes but the rate of UNCOALESCED 4-8 B accesses (one L1 wavefront
+//  each, ~1.5e11/s measured): the design minimises those -- per signature one RED and one table look-up, per
+//  survivor one returning atomic and one 8 B store, per member of a kept cluster one record gather.
+//    k_indel_hist      8 B/sig read (chrom, a)                 + one RED per signature
+//    k_bucket_prefix   4 B/bucket read, 4 B/bucket written     flag + slot offset inside the 4096-bucket tile
+//    k_scan_small      tile totals -> tile bases               (a few thousand words, one CTA)
+//    k_indel_scatter   8 B/sig read + one look-up              -> (key, index) 8 B per survivor, bucket order
+//    k_bucket_fixup    8 B/survivor read + written             in-bucket order (+ clears the histogram)
+//    k_select_heads    4 B/survivor read (chain votes)         -> 16-20 B record per member of a kept cluster
+// ------------------------------------------------------------------------------------------
+static constexpr int FIX_SMALL = 64;                    // buckets with more survivors than this are ordered by a CTA (k_bucket_fixup_big)
+static constexpr int BP_PER = 16, BP_TILE = 256 * BP_PER;   // buckets per tile of k_bucket_prefix
+static constexpr int BP_TILE_SHIFT = 12;
+static_assert((1 << BP_TILE_SHIFT) == BP_TILE, "tile size");
+static constexpr uint32_t BP_NONE = 0xffffffffu;        // bpre[] of a bucket that is not flagged
+
+__device__ __forceinline__ uint32_t indel_key32(int32_t c, int32_t raw, int is_ins, const ContigTab& ct, uint32_t& bad) {
+    if (c < 0 || c >= ct.n) { bad |= ST_BAD_CHROM; return 0u; }
+    const int64_t pos = is_ins ? (raw >> 1) : raw;
+    if (raw < 0 || pos > ct.len[c]) { bad |= ST_BAD_POS; return 0u; }   // len < 0: contig not owned by this shard
+    return (uint32_t)(ct.off[c] + (uint64_t)pos);
+}
+
+__global__ void __launch_bounds__(256) k_indel_hist(const int32_t* __restrict__ chrom, const int32_t* __restrict__ a, int64_t n, int is_ins,
+                                                    ContigTab ct, uint32_t* status, uint32_t* __restrict__ bkt) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const bool aligned = ((((uintptr_t)chrom) | ((uintptr_t)a)) & 15) == 0;
+    const int64_t nv = aligned ? (n >> 2) : 0;
+    uint32_t bad = 0;
+    for (int64_t v = tid; v < nv; v += stride) {
+        const int4 c4 = __ldcs(reinterpret_cast<const int4*>(chrom) + v), a4 = __ldcs(reinterpret_cast<const int4*>(a) + v);
+        const uint32_t k0 = indel_key32(c4.x, a4.x, is_ins, ct, bad), k1 = indel_key32(c4.y, a4.y, is_ins, ct, bad);
+        const uint32_t k2 = indel_key32(c4.z, a4.z, is_ins, ct, bad), k3 = indel_key32(c4.w, a4.w, is_ins, ct, bad);
+        atomicAdd(&bkt[(k0 >> BKT_SHIFT) + BKT_PAD], 1u); atomicAdd(&bkt[(k1 >> BKT_SHIFT) + BKT_PAD], 1u);
+        atomicAdd(&bkt[(k2 >> BKT_SHIFT) + BKT_PAD], 1u); atomicAdd(&bkt[(k3 >> BKT_SHIFT) + BKT_PAD], 1u);
+    }
+    for (int64_t i = nv * 4 + tid; i < n; i += stride) atomicAdd(&bkt[(indel_key32(chrom[i], a[i], is_ins, ct, bad) >> BKT_SHIFT) + BKT_PAD], 1u);
+    if (bad) atomicOr(status, bad);
+}
+
+// per bucket: bpre[b] = number of survivors in flagged buckets before b INSIDE its tile, or BP_NONE when the +-rb
+// bucket neighbourhood holds fewer than `need` signatures; tile_tot[tile] = survivors of the tile.  Buckets with
+// more than FIX_SMALL survivors are listed for the CTA-sized in-bucket pass.  Every tile is independent (no
+// look-back chain): one streaming read of the histogram, one streaming write of bpre.
+struct BigBuckets { uint4* list; uint32_t cap; uint32_t* count; };   // (tile, offset inside the tile, count, -)
+// RB in 1..8: neighbourhood radius known at compile time, every thread keeps its 16 buckets + halo (32 counts, eight
+// 128-bit loads) in registers; RB == 0: any radius <= BKT_PAD through a shared-memory tile.
+template <int RB>
+__global__ void __launch_bounds__(256) k_bucket_prefix(const uint32_t* __restrict__ bkt, uint32_t n_buckets, int rb, uint32_t need,
+                                                       uint32_t* __restrict__ bpre, uint32_t* __restrict__ tile_tot, BigBuckets BB,
+                                                       uint32_t* status) {
+    __shared__ uint32_t s_b[RB == 0 ? (BP_TILE + 2 * BKT_PAD + 8) * 17 / 16 + 8 : 1];
+    __shared__ uint32_t s_warp[9];
+    auto P = [](int i) { return i + (i >> 4); };   // +1 word per 16: threads stride 17 words -> no bank conflicts
+    const uint32_t n_tiles = (n_buckets + BP_TILE - 1) / BP_TILE;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t t0 = (int64_t)tile * BP_TILE;
+        const int l0 = threadIdx.x * BP_PER;
+        uint32_t mask = 0, mine = 0;
+        uint32_t own[BP_PER];
+        if (RB > 0) {
+            // w[k] = count of bucket t0 + l0 - 8 + k; (BKT_PAD - 8) words keep the 16 B alignment
+            uint32_t w[32];
+            const uint4* src = reinterpret_cast<const uint4*>(bkt + BKT_PAD + t0 + l0 - 8);
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const uint4 x = __ldg(src + k); w[4 * k] = x.x; w[4 * k + 1] = x.y; w[4 * k + 2] = x.z; w[4 * k + 3] = x.w; }
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 8 - RB; k <= 8 + RB; k++) sum += w[k];
+#pragma unroll
+            for (int j = 0; j < BP_PER; j++) {
+                own[j] = w[8 + j];
+                if (t0 + l0 + j < n_buckets && sum >= need) { mask |= 1u << j; mine += own[j]; }
+                if (j + 1 < BP_PER) sum += w[8 + j + RB + 1] - w[8 + j - RB];
+            }
+        } else {
+            for (int i = threadIdx.x; i < BP_TILE + 2 * rb + 1; i += 256) s_b[P(i)] = bkt[t0 - rb + i + BKT_PAD];
+            __syncthreads();
+            uint32_t sum = 0;
+            for (int k = 0; k <= 2 * rb; k++) sum += s_b[P(l0 + k)];
+#pragma unroll
+            for (int j = 0; j < BP_PER; j++) {
+                own[j] = s_b[P(l0 + j + rb)];
+                if (t0 + l0 + j < n_buckets && sum >= need) { mask |= 1u << j; mine += own[j]; }
+                sum += s_b[P(l0 + j + 2 * rb + 1)] - s_b[P(l0 + j)];
+            }
+        }
+        uint32_t total;
+        uint32_t run = block_excl_scan_256(mine, s_warp, &total);
+        if (threadIdx.x == 0) tile_tot[tile] = total;
+        uint32_t o[BP_PER];
+#pragma unroll
+        for (int j = 0; j < BP_PER; j++) {
+            o[j] = BP_NONE;
+            if (mask >> j & 1u) {
+                const uint32_t cnt = own[j];
+                o[j] = run;
+                if (cnt > FIX_SMALL) {
+                    const uint32_t q = atomicAdd(BB.count, 1u);
+                    if (q < BB.cap) BB.list[q] = make_uint4(tile, run, cnt, 0u); else atomicOr(status, ST_LIST_OVERFLOW);
+                }
+                run += cnt;
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(bpre + t0 + l0);   // bpre is sized to whole tiles
+#pragma unroll
+        for (int j = 0; j < BP_PER; j += 4) dst[j >> 2] = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        if (RB == 0) __syncthreads();
+    }
+}
+
+// exclusive scan of arr[0..n) by ONE CTA (n: a few thousand words), *total_out = sum
+__global__ void __launch_bounds__(1024) k_scan_small(uint32_t* arr, int64_t n, uint32_t* total_out) {
+    __shared__ uint32_t s_w[33];
+    __shared__ uint32_t s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? arr[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_w[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += y; }
+            s_w[lane] = wi - w;
+            if (lane == 31) s_w[32] = wi;
+        }
+        __syncthreads();
+        if (i < n) arr[i] = s_run + s_w[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += s_w[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = s_run;
+}
+
+// survivors into bucket order: slot = tile base + offset of the bucket inside its tile + (count of the bucket,
+// counted down by one returning atomic).  Afterwards every flagged bucket's count is zero again.
+__global__ void __launch_bounds__(256) k_indel_scatter(const int32_t* __restrict__ chrom, const int32_t* __restrict__ a, int64_t n, int is_ins,
+                                                       ContigTab ct, const uint32_t* __restrict__ bpre, const uint32_t* __restrict__ tile_base,
+                                                       uint32_t* __restrict__ bkt, uint2* __restrict__ pairs_out) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const bool aligned = ((((uintptr_t)chrom) | ((uintptr_t)a)) & 15) == 0;
+    const int64_t nv = aligned ? (n >> 2) : 0;
+    uint32_t dummy = 0;   // validated by k_indel_hist
+    auto place = [&](uint32_t key, uint32_t pre, int64_t i) {
+        const uint32_t bu = key >> BKT_SHIFT;
+        const uint32_t old = atomicSub(&bkt[bu + BKT_PAD], 1u);
+        pairs_out[__ldg(&tile_base[bu >> BP_TILE_SHIFT]) + pre + old - 1u] = make_uint2(key, (uint32_t)i);
+    };
+    for (int64_t v = tid; v < nv; v += stride) {
+        const int4 c4 = __ldcs(reinterpret_cast<const int4*>(chrom) + v), a4 = __ldcs(reinterpret_cast<const int4*>(a) + v);
+        const uint32_t k0 = indel_key32(c4.x, a4.x, is_ins, ct, dummy), k1 = indel_key32(c4.y, a4.y, is_ins, ct, dummy);
+        const uint32_t k2 = indel_key32(c4.z, a4.z, is_ins, ct, dummy), k3 = indel_key32(c4.w, a4.w, is_ins, ct, dummy);
+        // the four look-ups are independent: all in flight before the first is used
+        const uint32_t p0 = __ldg(&bpre[k0 >> BKT_SHIFT]), p1 = __ldg(&bpre[k1 >> BKT_SHIFT]);
+        const uint32_t p2 = __ldg(&bpre[k2 >> BKT_SHIFT]), p3 = __ldg(&bpre[k3 >> BKT_SHIFT]);
+        if (p0 != BP_NONE) place(k0, p0, 4 * v);
+        if (p1 != BP_NONE) place(k1, p1, 4 * v + 1);
+        if (p2 != BP_NONE) place(k2, p2, 4 * v + 2);
+        if (p3 != BP_NONE) place(k3, p3, 4 * v + 3);
+    }
+    for (int64_t i = nv * 4 + tid; i < n; i += stride) {
+        const uint32_t key = indel_key32(chrom[i], a[i], is_ins, ct, dummy);
+        const uint32_t pre = __ldg(&bpre[key >> BKT_SHIFT]);
+        if (pre != BP_NONE) place(key, pre, i);
+    }
+}
+
+// order inside every bucket: destination = bucket start + number of bucket members with a smaller (key, slot).
+// A CTA stages 2048 slots + a halo of FIX_SMALL on both sides in shared memory (coalesced), every thread ranks its
+// 8 slots against their buckets there.  Buckets of more than FIX_SMALL survivors: k_bucket_fixup_big.  Rides along:
+// the bucket histogram is cleared for the next call (flagged buckets were counted down to zero, the others not).
+static constexpr int FX_TILE = 2048;
+__global__ void __launch_bounds__(256) k_bucket_fixup(const uint2* __restrict__ pairs, const uint32_t* n_dev, uint32_t* __restrict__ keys_out,
+                                                      uint32_t* __restrict__ idx_out, uint32_t* __restrict__ bkt, int64_t n_bkt) {
+    __shared__ uint32_t s_k[FX_TILE + 2 * FIX_SMALL];
+    {
+        uint4* b4 = reinterpret_cast<uint4*>(bkt);   // n_bkt is a multiple of 4, cudaMalloc alignment
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < (n_bkt >> 2); i += (int64_t)gridDim.x * 256) b4[i] = z;
+    }
+    const int64_t n = *n_dev;
+    const int64_t n_tiles = (n + FX_TILE - 1) / FX_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * FX_TILE;
+        for (int q = threadIdx.x; q < FX_TILE + 2 * FIX_SMALL; q += 256) {
+            const int64_t i = base - FIX_SMALL + q;
+            s_k[q] = (i >= 0 && i < n) ? pairs[i].x : 0u;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int j = 0; j < FX_TILE / 256; j++) {
+            const int q = FIX_SMALL + j * 256 + threadIdx.x;      // position in s_k
+            const int64_t i = base + j * 256 + threadIdx.x;
+            if (i >= n) continue;
+            const uint32_t key = s_k[q], bu = key >> BKT_SHIFT;
+            int lo = q, hi = q + 1, seen = 1;
+            uint32_t rank = 0;
+            const int qmin = (int)(base - FIX_SMALL < 0 ? FIX_SMALL - base : 0);                       // first valid position
+            const int64_t last = n - (base - FIX_SMALL);                                               // one past the last valid position
+            const int qmax = (int)(last < FX_TILE + 2 * FIX_SMALL ? last : FX_TILE + 2 * FIX_SMALL);
+            while (lo > qmin && seen <= FIX_SMALL) {
+                const uint32_t k = s_k[lo - 1];
+                if ((k >> BKT_SHIFT) != bu) break;
+                rank += k <= key ? 1u : 0u;     // earlier slot: smaller (key, slot) iff key <= mine
+                lo--; seen++;
+            }
+            while (hi < qmax && seen <= FIX_SMALL) {
+                const uint32_t k = s_k[hi];
+                if ((k >> BKT_SHIFT) != bu) break;
+                rank += k < key ? 1u : 0u;
+                hi++; seen++;
+            }
+            if (seen > FIX_SMALL) continue;     // a big bucket: ordered by k_bucket_fixup_big
+            const int64_t dst = base - FIX_SMALL + lo + rank;
+            keys_out[dst] = key;
+            idx_out[dst] = pairs[i].y;
+        }
+        __syncthreads();
+    }
+}
+// big buckets (pile-ups): one CTA per bucket, counting sort on the low BKT_SHIFT bits of the key
+__global__ void __launch_bounds__(256) k_bucket_fixup_big(const uint2* __restrict__ pairs, BigBuckets BB, const uint32_t* __restrict__ tile_base,
+                                                          uint32_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
+    constexpr int NB = 1 << BKT_SHIFT;
+    static_assert(NB == 256, "one histogram bin per thread");
+    __shared__ uint32_t s_cnt[NB];
+    __shared__ uint32_t s_warp[9];
+    const uint32_t n_list = min(*BB.count, BB.cap);
+    for (uint32_t q = blockIdx.x; q < n_list; q += gridDim.x) {
+        const uint4 e = BB.list[q];
+        const uint32_t first = tile_base[e.x] + e.y, cnt = e.z;
+        s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += 256) atomicAdd(&s_cnt[pairs[first + i].x & (NB - 1)], 1u);
+        __syncthreads();
+        uint32_t total;
+        const uint32_t ex = block_excl_scan_256(s_cnt[threadIdx.x], s_warp, &total);
+        s_cnt[threadIdx.x] = ex;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += 256) {
+            const uint2 pr = pairs[first + i];
+            const uint32_t dst = first + atomicAdd(&s_cnt[pr.x & (NB - 1)], 1u);
+            keys_out[dst] = pr.x;
+            idx_out[dst] = pr.y;
+        }
+        __syncthreads();
+    }
+}
+
 // small types: three sort keys per signature (name, second coordinate, primary)
 __global__ void k_other_keys(const int32_t* __restrict__ chrom, const int32_t* __restrict__ a, const int32_t* __restrict__ b,
                              const int32_t* __restrict__ rid, const int32_t* __restrict__ c, int64_t n, int svtype, ContigTab ct,
@@ -325,17 +641,42 @@ __global__ void k_other_keys(const int32_t* __restrict__ chrom, const int32_t* _
         uint32_t bad = 0;
         const int32_t ch = chrom[i], ai = a[i], bi = b[i], ri = rid[i], ci = c ? c[i] : 0;
         if (ch < 0 || ch >= ct.n) bad |= ST_BAD_CHROM;
+        else if (ct.len[ch] < 0) bad |= ST_BAD_POS;   // contig not owned by this shard
         if (ai < 0 || bi < 0 || ri < 0 || ci < 0) bad |= ST_NEG_FIELD;
         if (svtype == CSV_TRA && (ci >> 2) >= ct.n) bad |= ST_BAD_CHROM;
         if (svtype == CSV_INV && ci > 1) bad |= ST_NEG_FIELD;
         if (bad) atomicOr(status, bad);
-        k_rid[i] = (uint32_t)ri;
-        k_b[i] = (uint32_t)bi;
+        if (k_rid) { k_rid[i] = (uint32_t)ri; k_b[i] = (uint32_t)bi; }
         // (chr, a) for DUP cuteSV:783; (chr, strand, bp1) for INV cuteSV:792; (chr1, chr2, type, pos1) for TRA :801
         uint64_t hi = (uint64_t)(uint32_t)ch;
         if (svtype == CSV_INV) hi = hi * 2 + (uint32_t)ci;
-        if (svtype == CSV_TRA) hi = (hi << 20) | (uint32_t)ci;   // chr2*4+type < 2^20
+        if (svtype == CSV_TRA) hi = hi * (uint64_t)(4 * ct.n) + (uint32_t)ci;   // chr2*4+type < 4*n_contigs
         k_prim[i] = (hi << 31) | (uint32_t)ai;                     // a < 2^31
+    }
+}
+
+// Small types, second half of the tuple order: `perm` is sorted by the primary key only; inside every run of
+// equal primary keys order by (b, name, input index) -- the rest of the reference's sort key (cuteSV:783,792,801) --
+// by ranking each element against its run.  Runs are short (reads that report the same breakpoint); a run longer
+// than RUN_MAX sets ST_BIG_RUN and the host reruns the type with the chained-sorts path.
+static constexpr int RUN_MAX = 2048;
+__global__ void __launch_bounds__(256) k_run_fixup(const uint64_t* __restrict__ kprim_sorted, const uint32_t* __restrict__ perm, int64_t n,
+                                                   const int32_t* __restrict__ b, const int32_t* __restrict__ rid,
+                                                   uint32_t* __restrict__ perm_out, uint32_t* status) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = kprim_sorted[i];
+        const uint32_t x = perm[i];
+        const bool alone = (i == 0 || kprim_sorted[i - 1] != k) && (i + 1 >= n || kprim_sorted[i + 1] != k);
+        if (alone) { perm_out[i] = x; continue; }
+        const int32_t bx = b[x], rx = rid[x];
+        int64_t lo = i, hi = i + 1;
+        uint32_t rank = 0;
+        int seen = 1;
+        auto less = [&](uint32_t y) { const int32_t by = b[y], ry = rid[y]; return by < bx || (by == bx && (ry < rx || (ry == rx && y < x))); };
+        while (lo > 0 && kprim_sorted[lo - 1] == k && seen <= RUN_MAX) { rank += less(perm[lo - 1]) ? 1u : 0u; lo--; seen++; }
+        while (hi < n && kprim_sorted[hi] == k && seen <= RUN_MAX) { rank += less(perm[hi]) ? 1u : 0u; hi++; seen++; }
+        if (seen > RUN_MAX) { atomicOr(status, ST_BIG_RUN); perm_out[i] = x; continue; }
+        perm_out[lo + rank] = x;
     }
 }
 
@@ -599,7 +940,7 @@ __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const
             w[j] = 0; cnt[j] = 0;
             const int64_t r = base + j * 256 + threadIdx.x;
             if (r >= n_reads) continue;
-            if (ch[j] < 0 || ch[j] >= G.ct.n) { atomicOr(status, ST_BAD_CHROM); continue; }
+            if (ch[j] < 0 || ch[j] >= G.ct.n || G.ct.len[ch[j]] < 0) { atomicOr(status, ST_BAD_CHROM); continue; }   // len < 0: outside the shard
             if (!G.has_rows[ch[j]]) G.has_rows[ch[j]] = 1;
             if (!pr[j]) continue;
             const uint64_t off = G.ct.off[ch[j]];

@@ -78,8 +78,7 @@ template <typename K, bool IOTA>
 __global__ void __launch_bounds__(RS_THREADS, 4) k_rs_onesweep(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                             K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                             int64_t n_host, const uint32_t* n_dev, int shift,
-                                                            const uint32_t* __restrict__ gbase, uint64_t* status,
-                                                            uint32_t gen, uint32_t* ticket) {
+                                                            const uint32_t* __restrict__ gbase, TileSync ts) {
     constexpr int ITEMS = RsTraits<K>::ITEMS;
     constexpr int TILE = RS_THREADS * ITEMS;
     __shared__ uint32_t s_warp_hist[RS_WARPS][256];
@@ -91,8 +90,10 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_rs_onesweep(const K* __restri
     __shared__ uint32_t s_tile;
 
     const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
+    const uint32_t gen = ts_gen(ts);
+    uint64_t* const status = ts.status;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    if (tid == 0) s_tile = atomicAdd(ts.ticket, 1u);
     for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
     __syncthreads();
     const int tile = (int)s_tile;

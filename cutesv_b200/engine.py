@@ -25,6 +25,9 @@ class Engine(object):
         if getattr(self, "h", None):
             self.L.csv_destroy(self.h)
             self.h = None
+        for p in getattr(self, "_pinned", []):
+            self.L.csv_host_free(p)
+        self._pinned = []
 
     def __del__(self):
         try:
@@ -50,15 +53,33 @@ class Engine(object):
 
     # -- device-resident path (bench `value`): upload once, cluster many times --
 
-    def upload(self, sigs, reads):
+    def upload(self, sigs, reads, grouped=False):
+        """Asynchronous H2D of the inputs of cluster_device().  grouped=True: dicts from _abi.group_by_contig (rows grouped by
+        contig + `contig_off` instead of the contig column; csv_upload_*_grouped)."""
         keep = []
         for t, name in enumerate(_abi.TYPE_NAMES):
-            s, k = _abi.make_sig_cols(sigs.get(name))
-            keep.append(k)
-            _lib.check(self.L.csv_upload_sigs(self.h, t, C.byref(s)))
-        r, rk = _abi.make_reads_cols(reads)
-        keep.append(rk)
-        _lib.check(self.L.csv_upload_reads(self.h, C.byref(r)))
+            if grouped:
+                s, off, k = _abi.make_sig_cols_grouped(sigs.get(name))
+                keep.append((k, off))
+                if off is not None:
+                    _lib.check(self.L.csv_upload_sigs_grouped(self.h, t, C.byref(s), off.ctypes.data_as(C.POINTER(C.c_int64))))
+                else:
+                    _lib.check(self.L.csv_upload_sigs(self.h, t, C.byref(s)))
+            else:
+                s, k = _abi.make_sig_cols(sigs.get(name))
+                keep.append(k)
+                _lib.check(self.L.csv_upload_sigs(self.h, t, C.byref(s)))
+        if grouped:
+            r, r_off, rk = _abi.make_reads_cols_grouped(reads)
+            keep.append((rk, r_off))
+            if r_off is not None:
+                _lib.check(self.L.csv_upload_reads_grouped(self.h, C.byref(r), r_off.ctypes.data_as(C.POINTER(C.c_int64))))
+            else:
+                _lib.check(self.L.csv_upload_reads(self.h, C.byref(r)))
+        else:
+            r, rk = _abi.make_reads_cols(reads)
+            keep.append(rk)
+            _lib.check(self.L.csv_upload_reads(self.h, C.byref(r)))
         self._keep = keep  # host buffers must outlive the async copies
 
     def upload_alignments(self, aln):
@@ -152,13 +173,103 @@ class Engine(object):
         return dict(status=v[0], n_cand=v[1], n_names=v[2], max_support=v[3], kept=dict(zip(t, v[4:9])), big=dict(zip(t, v[9:14])),
                     giant=dict(zip(t, v[14:19])), pairs=v[19], domain=dict(zip(t, v[20:25])), members=dict(zip(t, v[25:30])))
 
+    def kernel_times(self):
+        """{kernel name: (launches, total ms)} of the calls made while profiling was on (collected by fetch())."""
+        need = int(self.L.csv_kernel_times(self.h, None, 0))
+        buf = C.create_string_buffer(need + 16)
+        self.L.csv_kernel_times(self.h, buf, need + 16)
+        out = {}
+        for ln in buf.value.decode().splitlines():
+            nm, n, ms = ln.split("\t")
+            out[nm] = (int(n), float(ms))
+        return out
+
     def launch_count(self):
         return int(self.L.csv_launch_count(self.h))
+
+    def graph_replays(self):
+        return int(self.L.csv_graph_replays(self.h))
+
+    # -- multi-GPU: contig shards + one NCCL all-gather of the final records --
+
+    def set_shard(self, owned):
+        """owned: bool/uint8 mask over contig ids (None = all contigs)."""
+        if owned is None:
+            _lib.check(self.L.csv_set_shard(self.h, None))
+            return
+        m = np.ascontiguousarray(owned, dtype=np.uint8)
+        assert len(m) == self.n_contigs
+        _lib.check(self.L.csv_set_shard(self.h, m.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        _lib.check(self.L.csv_comm_unique_id(buf, 128))
+        return buf.raw
+
+    def comm_init(self, uid, rank, world):
+        buf = C.create_string_buffer(bytes(uid), 128)
+        _lib.check(self.L.csv_comm_init(self.h, buf, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+
+    def comm_destroy(self):
+        _lib.check(self.L.csv_comm_destroy(self.h))
+
+    def allgather(self):
+        """Asynchronous, collective: pack + ONE ncclAllGather + device merge of the records of the last cluster_device()."""
+        _lib.check(self.L.csv_allgather(self.h))
+
+    def gathered_counts(self):
+        nc, nn = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.L.csv_gathered_counts(self.h, C.byref(nc), C.byref(nn)))
+        return nc.value, nn.value
+
+    def fetch_gathered(self, out=None):
+        nc, nn = self.gathered_counts()
+        if out is not None:
+            cands, genos, names = out
+        else:
+            cands = np.zeros(max(nc, 1), dtype=_abi.CAND_DTYPE)
+            genos = np.zeros(max(nc, 1), dtype=_abi.GENO_DTYPE)
+            names = np.zeros(max(nn, 1), dtype=np.int32)
+        _lib.check(self.L.csv_fetch_gathered(self.h, cands.ctypes.data_as(C.c_void_p), genos.ctypes.data_as(C.c_void_p), C.c_int64(len(cands)),
+                                             _abi.ptr(names), C.c_int64(len(names))))
+        return cands[:nc], genos[:nc], names[:nn]
 
     def device_ptrs(self):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _lib.check(self.L.csv_result_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+
+def _pin_packet_method(self, packed):
+    """Copy of an alignment packet in page-locked host memory (csv_host_alloc), so that csv_extract's H2D copies run at PCIe
+    speed and asynchronously.  The buffers are freed by close()."""
+    if not hasattr(self, "_pinned"):
+        self._pinned = []
+
+    def pin(a):
+        a = np.ascontiguousarray(a)
+        p = C.c_void_p()
+        _lib.check(self.L.csv_host_alloc(C.byref(p), C.c_size_t(max(a.nbytes, 1))))
+        self._pinned.append(p)
+        buf = (C.c_char * max(a.nbytes, 1)).from_address(p.value)
+        out = np.frombuffer(buf, dtype=a.dtype, count=a.size).reshape(a.shape)
+        out[...] = a
+        return out
+
+    out = {}
+    for k, v in packed.items():
+        if k == "sa":
+            out[k] = {kk: pin(np.asarray(vv, dtype=np.int32)) for kk, vv in v.items()}
+        elif k in ("cigar_off", "sa_off"):
+            out[k] = pin(np.asarray(v, dtype=np.int64))
+        elif k == "cigar":
+            out[k] = pin(np.asarray(v, dtype=np.uint32))
+        elif isinstance(v, np.ndarray) and v.dtype.kind in "iu" and k in ("chrom", "ref_start", "ref_end", "flag", "mapq", "query_len", "read_id"):
+            out[k] = pin(np.asarray(v, dtype=np.int32))
+        else:
+            out[k] = v
+    return out
 
 
 def _extract_method(self, packed):
@@ -209,5 +320,6 @@ def _fetch_extracted_method(self):
     return dict(sigs=sigs, piece_off=poff, piece_cnt=pcnt, pieces=pieces[:npz.value], rows=rows)
 
 
+Engine.pin_packet = _pin_packet_method
 Engine.extract = _extract_method
 Engine.fetch_extracted = _fetch_extracted_method

@@ -60,6 +60,49 @@ def globalize_aux(cands, index):
     return cands
 
 
+def globalize_aux_by_rank(cands, index_by_rank):
+    """Gathered records (csv_fetch_gathered): csv_cand.reserved[1] is the source rank; rewrite the aux of INS rows from that
+    rank's shard-local signature index to the index in the full arrays.  index_by_rank[r] = shard index table of rank r."""
+    m = cands["svtype"] == _abi.CSV_INS
+    if not m.any():
+        return cands
+    cands = cands.copy()
+    src = cands["reserved"][:, 1]
+    for r, idx in enumerate(index_by_rank):
+        mm = m & (src == r)
+        if mm.any():
+            cands["aux"][mm] = idx[cands["aux"][mm]]
+    return cands
+
+
+def owned_mask(owner, rank):
+    return (np.asarray(owner) == rank).astype(np.uint8)
+
+
+def run_sharded(eng, cfg, rank, world, repeats=1, type_mask=None):
+    """One genome on `world` GPUs through the product API: LPT contig shards, csv_set_shard, device-resident pipeline,
+    csv_allgather.  eng: an Engine with csv_comm_init done.  Returns dict(results=[merged (cands, genos, names) per repeat],
+    index=shard index tables, owner=contig -> rank)."""
+    owner = lpt_assign(contig_weights(cfg["sigs"], len(cfg["lens"])), world)
+    sigs, reads, index = shard_inputs(cfg["sigs"], cfg["reads"], owner, rank)
+    eng.set_shard(owned_mask(owner, rank))
+    if type_mask is None:
+        type_mask = sum(1 << _abi.TYPE_IDS[k] for k in cfg["sigs"])
+    if "TRA" in cfg["sigs"] and cfg["params"].get("genotype"):
+        # the TRA genotyper scans BAM-order alignment records around pos1 (own contig) AND pos2 (any contig): whole table
+        r = cfg["reads"]
+        order = np.lexsort((np.arange(len(r["chrom"])), r["start"], r["chrom"]))
+        eng.upload_alignments({k: v[order] for k, v in r.items()})
+    eng.upload(sigs, reads)
+    out = []
+    for _ in range(repeats):
+        eng.cluster_device(type_mask)
+        eng.counts()
+        eng.allgather()
+        out.append(eng.fetch_gathered())
+    return dict(results=out, index=index, owner=owner)
+
+
 def merge_results(parts):
     """parts: list over ranks of (cands, genos, names).  Returns one result in the single-GPU
     order: svtype, contig id, emission order (per-contig order is preserved inside every part)."""

@@ -556,6 +556,35 @@ def synth_cigar_packet(n_reads, mean_indels=850, seed=5, n_contigs=25, sa_frac=0
                query_len=qlen.astype(np.int32), read_id=np.arange(n_reads, dtype=np.int32), cigar_off=off.astype(np.int64),
                sa_off=np.zeros(n_reads + 1, dtype=np.int64), cigar=cigar,
                sa={k2: np.zeros(0, np.int32) for k2 in ("chrom", "pos0", "strand", "mapq", "first_clip", "last_clip", "ref_span")})
+    if sa_frac > 0:
+        # sa_frac of the records carry 1-6 supplementary segments (BASELINE config 5: "dense SA-tag splits"): the query is cut
+        # into consecutive pieces, the primary keeps the first one; segments land near the primary (DEL / INS / DUP / INV shaped)
+        # or on another contig (TRA shaped)
+        has = rng.random(n_reads) < sa_frac
+        n_seg = np.where(has, rng.integers(1, 7, n_reads), 0).astype(np.int64)
+        sa_off = np.concatenate([[0], np.cumsum(n_seg)])
+        S = int(sa_off[-1])
+        owner = np.repeat(np.arange(n_reads), n_seg)
+        k_in = np.arange(S, dtype=np.int64) - np.repeat(sa_off[:-1], n_seg)
+        ql = qlen[owner]
+        piece = np.maximum(ql // (n_seg[owner] + 1), 1)
+        first_clip = piece * (k_in + 1)                       # query consumed before this segment
+        last_clip = np.maximum(ql - first_clip - piece, 0)
+        far = rng.random(S) < 0.25
+        sa_chrom = np.where(far, rng.integers(0, len(lens), S), chrom[owner]).astype(np.int64)
+        jitter = rng.integers(-3000, 3000, S)
+        near_pos = start[owner] + (span[owner] * (k_in + 1)) // (n_seg[owner] + 1) + jitter
+        sa_span = np.maximum(piece + rng.integers(-20, 20, S), 1)
+        pos0 = np.where(far, (rng.random(S) * np.maximum(lens[sa_chrom] - sa_span - 1, 1)).astype(np.int64), near_pos)
+        pos0 = np.clip(pos0, 0, np.maximum(lens[sa_chrom] - sa_span - 1, 0))
+        same = (out["flag"][owner] == 16).astype(np.int64)
+        strand = np.where(rng.random(S) < 0.8, same, 1 - same)
+        out["sa_off"] = sa_off.astype(np.int64)
+        out["sa"] = dict(chrom=sa_chrom.astype(np.int32), pos0=pos0.astype(np.int32), strand=strand.astype(np.int32),
+                         mapq=np.where(rng.random(S) < 0.9, 60, 5).astype(np.int32), first_clip=first_clip.astype(np.int32),
+                         last_clip=last_clip.astype(np.int32), ref_span=sa_span.astype(np.int32))
+        # the primary of a split read is soft-clipped at its end by what the segments consume
+        # (the CIGAR stays as generated: the clip only matters to the split-read engine through query_len / segment bounds)
     return out, names, lens
 
 

@@ -116,7 +116,7 @@ typedef struct csv_cand {
     int32_t names_cnt;
     int32_t cluster;    /* ordinal of the chain-linkage cluster this row came from */
     int32_t flags;      /* CSV_F_* */
-    int32_t reserved[2];
+    int32_t reserved[2]; /* [1]: source rank of a record returned by csv_fetch_gathered */
 } csv_cand;
 
 /* assign_gt()/cal_GL() result (cuteSV_genotype.py:33-56,161-173), 40 B. */
@@ -268,12 +268,46 @@ int csv_fetch_read_rows(csv_ctx* ctx, int64_t cap, int32_t* chrom, int32_t* star
 /* Profiling: per-stage device milliseconds of the last csv_cluster / csv_extract call. */
 int csv_set_profiling(csv_ctx* ctx, int on);
 int csv_stage_ms(csv_ctx* ctx, float ms[CSV_ST_COUNT]);
+/* Per-kernel totals of the last profiled call(s): with profiling on, every kernel launch sits between its own
+ * pair of CUDA events on its launching stream; one text line per kernel, "name<TAB>launches<TAB>total_ms".
+ * Returns the buffer size the text needs (incl. NUL). */
+int64_t csv_kernel_times(csv_ctx* ctx, char* buf, int64_t cap);
 /* SV types are independent until the final ordering (the reference runs them as separate Pool#3
  * tasks, cuteSV:1113-1199); by default each type's kernel chain runs on its own stream ("lane").
  * on = 0 serialises the types on the ctx stream, e.g. to time every kernel alone. */
 int csv_set_lanes(csv_ctx* ctx, int on);
-/* Number of kernels the library launched since the ctx was created. */
+/* Number of kernels the library launched since the ctx was created (kernels inside a replayed CUDA graph count). */
 int64_t csv_launch_count(csv_ctx* ctx);
+/* csv_cluster calls served by replaying a captured CUDA graph.  A call whose inputs are already device resident
+ * replays the graph of its (type_mask, sizes, params) from its third occurrence on; CUTESV_B200_GRAPHS=0 disables. */
+int64_t csv_graph_replays(csv_ctx* ctx);
+
+/* ---- multi-GPU: contigs sharded over ranks, one csv_ctx per GPU / process -------------------------------------
+ * Every resolution_* call of the reference is keyed by (svtype, chr) and reads only that contig's signatures and
+ * reads-table rows (cuteSV:1116-1189; resolveINDEL.py:52-54,445-447), so contigs are independent units: each rank
+ * runs the whole pipeline on its contigs with no data-path collective, and ONE NCCL all-gather of the final
+ * records assembles the result on every rank in the single-GPU order.  (The reference's Pool(threads).map_async
+ * over (type, chr) tasks, cuteSV:1113-1199, is the CPU counterpart.) */
+
+/* owned[k] != 0: contig k belongs to this ctx's shard (NULL = all).  Contigs outside the shard take no room in the
+ * linear coordinate, so histogram / bin tables scale with the shard; a signature or reads-table row on such a
+ * contig is an input error (CSV_E_INPUT).  Contig ids stay global.  Call after csv_set_contigs. */
+int csv_set_shard(csv_ctx* ctx, const uint8_t* owned);
+/* ncclGetUniqueId: rank 0 calls it and ships the bytes (>= 128) to the other ranks by any means. */
+int csv_comm_unique_id(void* id, size_t bytes);
+/* ncclCommInitRank on the ctx's device.  Collective: every rank calls it with the same id. */
+int csv_comm_init(csv_ctx* ctx, const void* id, int rank, int world);
+int csv_comm_destroy(csv_ctx* ctx);
+/* After csv_cluster, asynchronous on the ctx stream, collective: packs this rank's records (csv_cand, csv_geno,
+ * supporting read ids) into one padded message, ONE ncclAllGather over NVLink, then merges the messages of all
+ * ranks on the device into the single-GPU order (svtype, contig id, emission order).  csv_cand.reserved[1] of a
+ * gathered record is its source rank (csv_cand.aux of an INS row indexes THAT rank's INS signatures).  The padded
+ * message size is agreed once (first call: one count all-reduce) and re-agreed only when a rank outgrows it. */
+int csv_allgather(csv_ctx* ctx);
+/* Blocks until the gather finished; total sizes over all ranks. */
+int csv_gathered_counts(csv_ctx* ctx, int64_t* n_cand, int64_t* n_names);
+int csv_fetch_gathered(csv_ctx* ctx, csv_cand* cands, csv_geno* genos, int64_t cap_cand, int32_t* names, int64_t cap_names);
+int csv_gathered_device_ptrs(csv_ctx* ctx, const csv_cand** cands, const csv_geno** genos, const int32_t** names);
 /* Device counters of the last finished csv_cluster call, 32 words: [0] status, [1] candidates,
  * [2] names, [3] max support, [4..8] kept clusters per type, [9..13] CTA-class clusters,
  * [14..18] global-scratch-class clusters, [19] (read, window) pairs, [20..24] sorted-domain size per

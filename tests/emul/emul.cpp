@@ -66,7 +66,7 @@ void run_indel(Ctx& cx, const csv_sig_cols& S, int t, uint32_t& kslot) {
     std::iota(sidx.begin(), sidx.end(), 0u);
     std::stable_sort(sidx.begin(), sidx.end(), [&](uint32_t x, uint32_t y) { return key[x] < key[y]; });
     ClusterParams C = cluster_params(cx.P, t);
-    IndelView V{S.chrom, S.a, S.b, S.read_id, S.c, sidx.data(), is_ins};
+    IndelView V{S.chrom, S.a, S.b, S.read_id, S.c, sidx.data(), is_ins, nullptr, nullptr};
     Emit E = make_emit(cx);
     std::vector<char> arena;
     int64_t red[8];

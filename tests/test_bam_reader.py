@@ -129,3 +129,36 @@ def test_errors(tmp_path):
     with pytest.raises(IOError):
         rd.index_statistics()
     rd.close()
+
+
+def test_close_before_eof_and_bgzf_non_bam(tmp_path):
+    """Destroying a reader while a read-ahead batch is still inflating, and opening a BGZF file that is not BAM
+    (a bgzipped text file): both used to free the batch under the inflate workers."""
+    import gzip
+    import struct
+    import zlib
+    reads, contigs = _sorted_reads(5, 1500, with_seq=True)
+    path = str(tmp_path / "big.bam")
+    bam_writer.write_bam(path, contigs, reads, block_bytes=4000)
+    chrom_id = {n: i for i, n in enumerate(sorted(n for n, _ in contigs))}
+    for _ in range(20):
+        rd = bamio.BamReader(path, threads=4)
+        rd.tune(4, -1)          # small batches: several are still ahead of the parser at close()
+        rd.set_chrom_ids(chrom_id)
+        assert rd.next_packet(10) is not None
+        rd.close()
+    # a BGZF container whose payload is text (e.g. a .vcf.gz): many blocks so that the read-ahead is busy when open fails
+    def bgzf_block(data):
+        comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = comp.compress(data) + comp.flush()
+        head = b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(body) + 25)
+        return head + body + struct.pack("<II", zlib.crc32(data), len(data))
+    txt = str(tmp_path / "x.vcf.gz")
+    with open(txt, "wb") as f:
+        for i in range(300):
+            f.write(bgzf_block((b"##line %d of a text file\n" % i) * 500))
+        f.write(bgzf_block(b""))
+    assert bamio.is_bam(txt)   # BGZF magic only
+    for _ in range(10):
+        with pytest.raises(Exception):
+            bamio.BamReader(txt, threads=4)
