@@ -43,6 +43,14 @@ _SIGNATURES = {
     "csv_cal_gl": (C.c_int, [_VP, _I32P, _I32P, C.c_int64, _VP]),
     "csv_extract": (C.c_int, [_VP, C.POINTER(_abi.csv_read_cols), C.POINTER(C.c_uint32), C.c_int64,
                               C.POINTER(_abi.csv_sa_cols), _I64P, _I64P]),
+    "csv_extract_append": (C.c_int, [_VP, C.POINTER(_abi.csv_read_cols), C.POINTER(C.c_uint32), C.c_int64,
+                                     C.POINTER(_abi.csv_sa_cols), _I64P, _I64P]),
+    "csv_extract_reset": (C.c_int, [_VP]),
+    "csv_extract_skipped": (C.c_int64, [_VP]),
+    "csv_remap_read_ids": (C.c_int, [_VP, _I32P, C.c_int64]),
+    "csv_swap_ins_rows": (C.c_int, [_VP, _I64P, C.c_int64]),
+    "csv_fetch_sigs_range": (C.c_int, [_VP, C.c_int, C.c_int64, C.c_int64, _I32P, _I32P, _I32P, _I32P, _I32P, _I32P, _I32P]),
+    "csv_fetch_pieces_range": (C.c_int, [_VP, C.c_int64, C.c_int64, _I32P]),
     "csv_fetch_sigs": (C.c_int, [_VP, C.c_int, C.c_int64, _I32P, _I32P, _I32P, _I32P, _I32P, _I32P, _I32P]),
     "csv_fetch_pieces": (C.c_int, [_VP, C.c_int64, _I32P, _I64P]),
     "csv_fetch_read_rows": (C.c_int, [_VP, C.c_int64, _I32P, _I32P, _I32P, _I32P, C.POINTER(C.c_uint8)]),

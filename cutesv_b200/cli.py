@@ -117,16 +117,20 @@ def load_bed(bed_file, tasks):
 
 
 class _Accumulator(object):
-    """Extracted signature columns / reads rows of all packets (host), provisional read ids."""
+    """Host side of the scan: the extracted signatures and reads rows stay ON THE DEVICE (csv_extract_append); the host keeps
+    only what the device cannot hold -- INS sequence strings (rebuilt per packet from the piece descriptors), provisional
+    read ids, and the all-alignments table of the TRA genotyper."""
 
-    def __init__(self):
-        self.cols = {t: {k: [] for k in ("chrom", "a", "b", "read_id", "c")} for t in _abi.TYPE_NAMES}
+    def __init__(self, eng, min_siglength, merge_ins_threshold):
+        self.eng = eng
         self.ins_seq = []
-        self.rows = {k: [] for k in ("chrom", "start", "end", "read_id", "is_primary")}
+        self.rec_base = 0
         self.name_id = {}
         self.names = []
         self.aln = {k: [] for k in ("chrom", "start", "end", "read_id", "is_primary")}  # every record, BAM order
         self.aln_chunks = []
+        self.merge = (min_siglength, merge_ins_threshold)
+        eng.extract_reset()
 
     def rid(self, name):
         i = self.name_id.get(name)
@@ -136,17 +140,20 @@ class _Accumulator(object):
             self.names.append(name)
         return i
 
-    def add(self, ex, query_of, want_seq):
-        """ex: Engine.fetch_extracted(); query_of(rec) -> query sequence of record `rec` of the packet."""
-        for t in _abi.TYPE_NAMES:
-            for k in ("chrom", "a", "b", "read_id", "c"):
-                self.cols[t][k].append(ex["sigs"][t][k])
-        s = ex["sigs"]["INS"]
-        for i in range(len(s["chrom"])):
-            self.ins_seq.append(packing.ins_sequence(ex["pieces"], int(ex["piece_off"][i]), int(ex["piece_cnt"][i]),
-                                                     query_of) if want_seq else "")
-        for k in self.rows:
-            self.rows[k].append(ex["rows"][k])
+    def extract(self, packet, n_records, query_of, want_seq, cigar_of=None):
+        """One packet through csv_extract_append.  query_of(rec) -> query sequence of packet record `rec`;
+        cigar_of(rec) -> (uint32 CIGAR array, reference_start) for the rare signatures the host rebuilds."""
+        r = self.eng.extract(packet, append=True)
+        n_new = r["counts"]["INS"] - r["first"]["INS"]
+        if want_seq and n_new:
+            po, pc, pieces = self.eng.fetch_ins_pieces(r["first"]["INS"], n_new, r["first_pieces"], r["n_pieces"] - r["first_pieces"])
+            base = self.rec_base
+            for i in range(n_new):
+                self.ins_seq.append(packing.ins_sequence(pieces, int(po[i]), int(pc[i]), lambda rec: query_of(rec - base),
+                                                         (lambda rec: cigar_of(rec - base)) if cigar_of else None, self.merge))
+        else:
+            self.ins_seq.extend([""] * n_new)
+        self.rec_base += n_records
 
     def add_alignment(self, chrom_id, read):
         a = self.aln
@@ -168,9 +175,10 @@ class _Accumulator(object):
         order = np.argsort(a["chrom"], kind="stable")
         return {k: v[order] for k, v in a.items()}
 
-    def finish(self, names=None, rank=None):
-        """Concatenate and turn provisional read ids into ranks in Python string order.  The native
-        decoder keeps the name table itself and passes (names, rank)."""
+    def finish(self, names=None, rank=None, want_seq=True):
+        """Turn the provisional read ids on the device into ranks in Python string order (csv_remap_read_ids) and put INS rows
+        that tie on (contig, int(pos), len, read) into the order of their sequences (cuteSV:774).  The native decoder keeps
+        the name table itself and passes (names, rank).  Returns the read names in rank order."""
         if names is None:
             names = self.names
             order = sorted(range(len(names)), key=lambda i: names[i])
@@ -179,17 +187,46 @@ class _Accumulator(object):
         else:
             order = np.argsort(rank[:len(names)], kind="stable")
         sorted_names = [names[i] for i in order]
-        sigs = {}
-        for t in _abi.TYPE_NAMES:
-            c = {k: (np.concatenate(v) if v else np.zeros(0, np.int32)) for k, v in self.cols[t].items()}
-            c["read_id"] = rank[c["read_id"]] if len(c["read_id"]) else c["read_id"]
-            if t in ("DEL", "DUP"):
-                c["c"] = None
-            sigs[t] = c
-        r = {k: (np.concatenate(v) if v else np.zeros(0, np.uint8 if k == "is_primary" else np.int32)) for k, v in self.rows.items()}
-        r["read_id"] = rank[r["read_id"]] if len(r["read_id"]) else r["read_id"]
         self.rank = rank
-        return sigs, r, sorted_names
+        self.eng.remap_read_ids(rank[:max(len(names), 1)])
+        if want_seq and len(self.ins_seq) > 1:
+            c = self.eng.fetch_sig_cols("INS", cols=("chrom", "a", "b", "read_id"))
+            pairs = ins_tie_swaps(c["chrom"], c["a"], c["b"], c["read_id"], self.ins_seq)
+            if len(pairs):
+                self.eng.swap_ins_rows(pairs)
+                for i, j in pairs:
+                    self.ins_seq[i], self.ins_seq[j] = self.ins_seq[j], self.ins_seq[i]
+        return sorted_names
+
+
+def ins_tie_swaps(chrom, a, b, read_id, seqs):
+    """Row swaps that put INS rows tying on (contig, int(pos), len, read) into the order of their sequence strings, the last
+    field of the reference's INS sort key (cuteSV:774).  Vectorised search for tie groups (they need one read reporting two
+    insertions of equal length at the same position: rare), selection sort inside a group.  Returns a list of (i, j)."""
+    n = len(chrom)
+    if n < 2:
+        return []
+    pos = np.asarray(a, dtype=np.int64) >> 1
+    order = np.lexsort((np.arange(n), read_id, b, pos, chrom))
+    k = np.stack([np.asarray(chrom)[order], pos[order], np.asarray(b)[order], np.asarray(read_id)[order]])
+    same = np.all(k[:, 1:] == k[:, :-1], axis=0)
+    if not same.any():
+        return []
+    pairs = []
+    starts = np.flatnonzero(same & ~np.concatenate([[False], same[:-1]]))
+    for s0 in starts:
+        e = s0 + 1
+        while e < n - 1 and same[e]:
+            e += 1
+        rows = sorted(int(x) for x in order[s0:e + 1])          # input positions of the tie group, ascending
+        want = sorted(rows, key=lambda r: (seqs[r], r))         # which row's content belongs at each position
+        cur = list(rows)                                         # cur[p] = original row whose content sits at position rows[p]
+        for p in range(len(rows)):
+            if cur[p] != want[p]:
+                q = cur.index(want[p])
+                pairs.append((rows[p], rows[q]))
+                cur[p], cur[q] = cur[q], cur[p]
+    return pairs
 
 
 def main_ctrl(args, argv, engine=None):
@@ -220,14 +257,15 @@ def main_ctrl(args, argv, engine=None):
     eng = engine if engine is not None else Engine(int(os.environ.get("CUTESV_B200_DEVICE", "0")))
     eng.set_params(params)
     eng.set_contigs(np.array([lens[n] for n in chrom_names], dtype=np.int64))
-    acc = _Accumulator()
+    acc = _Accumulator(eng, args.min_siglength, args.merge_ins_threshold)
     want_seq = not args.ignore_sequence
     names_rank = source.scan(args, eng, acc, tasks, bed, chrom_id, want_seq)
     logging.info("Rebuilding signatures of structural variants.")
-    sigs, reads_cols, read_names = acc.finish(*names_rank)
+    read_names = acc.finish(*names_rank, want_seq=want_seq)   # the signatures never left the device
     logging.info("Clustering structural variants.")
     eng.upload_alignments(acc.alignments(acc.rank) if args.genotype else None)
-    cands, genos, names = eng.cluster(sigs, reads_cols)
+    eng.cluster_device(0x1F)
+    cands, genos, names = eng.fetch()
     eng.upload_alignments(None)
     got = rows.records_to_rows(cands, genos, names, chrom_names, lambda k: read_names[k], lambda k: acc.ins_seq[k], bool(args.genotype))
     results = {}
@@ -240,8 +278,9 @@ def main_ctrl(args, argv, engine=None):
     opts = dict(genotype=args.genotype, max_size=args.max_size, min_size=args.min_size, report_readid=args.report_readid,
                 ignore_sequence=args.ignore_sequence)
     vcf.write_vcf(args.output, results, reference, contig_info, args.sample, argv, opts)
-    if args.retain_work_dir:
-        _write_workdir(tmp, sigs, reads_cols, chrom_names, read_names, acc.ins_seq, args.write_old_sigs)
+    if args.retain_work_dir:   # the reference's pickle layout needs the signatures on the host: one D2H of the columns
+        sigs = {t: eng.fetch_sig_cols(t) for t in _abi.TYPE_NAMES}
+        _write_workdir(tmp, sigs, eng.fetch_read_rows(), chrom_names, read_names, acc.ins_seq, args.write_old_sigs)
     reference.close()
     source.close()
     return results
@@ -281,8 +320,8 @@ class _PysamSource(object):
             if not packet:
                 return
             pk = packing.pack_alignments(packet, chrom_id, _NameIds(acc))
-            eng.extract(pk)
-            acc.add(eng.fetch_extracted(), lambda rec: packet[rec].query_sequence, want_seq)
+            acc.extract(pk, len(packet), lambda rec: packet[rec].query_sequence, want_seq,
+                        lambda rec: (pk["cigar"][pk["cigar_off"][rec]:pk["cigar_off"][rec + 1]], int(pk["ref_start"][rec])))
 
         for i, task in enumerate(tasks):
             packet = []
@@ -357,8 +396,8 @@ class _NativeSource(object):
                     keep[m & ~hit] = False
             sub = bamio.subset_packet(pk, np.flatnonzero(keep))
             if len(sub["chrom"]):
-                eng.extract(sub)
-                acc.add(eng.fetch_extracted(), lambda rec: bamio.decode_seq(sub, rec), want_seq)
+                acc.extract(sub, len(sub["chrom"]), lambda rec: bamio.decode_seq(sub, rec), want_seq,
+                            lambda rec: (sub["cigar"][sub["cigar_off"][rec]:sub["cigar_off"][rec + 1]], int(sub["ref_start"][rec])))
             n_seen += len(keep)
             logging.info("Decoded %d records." % n_seen)
         return rd.names(), rd.name_ranks()

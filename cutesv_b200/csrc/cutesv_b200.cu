@@ -92,6 +92,9 @@ struct ExtractState {
     DBuf r[7], cigar_off, sa_off, cigar, s[7], piece_off, piece_cnt, pieces, counters;
     uint32_t* h_counters = nullptr;  // pinned
     uint32_t n_pieces = 0;
+    uint32_t n_records = 0;          // alignment records of all packets of the accumulation (record index base of INS pieces)
+    uint32_t n_skipped = 0;
+    bool appending = false;
 };
 static void extract_release(ExtractState* x) {
     for (int k = 0; k < 7; k++) { x->r[k].release(); x->s[k].release(); }
@@ -170,7 +173,7 @@ struct csv_ctx {
     uint32_t cap_cand = 0, cap_names = 0;
     Counters* h_counters = nullptr;  // pinned
     // genotype
-    DBuf bin_start, bin_fill, bin_bits, win_list, dr, has_rows, gl_table, pow_half, pairs;
+    DBuf bin_start, bin_fill, bin_bits, win_list, win_rec, dr, has_rows, gl_table, pow_half, pairs;
     uint32_t pow_n = 0;
     // state
     bool ran = false, counts_valid = false;
@@ -233,10 +236,8 @@ template <int KIND>
 static void launch_cluster_kind(csv_ctx* c, const TypeJob& J, const Emit& E, Counters* ctr, uint32_t* work, size_t smem_warp) {
     static const char* const nm_w[4] = {"k_cluster_warp<INDEL>", "k_cluster_warp<DUP>", "k_cluster_warp<INV>", "k_cluster_warp<TRA>"};
     static const char* const nm_b[4] = {"k_cluster_block<INDEL>", "k_cluster_block<DUP>", "k_cluster_block<INV>", "k_cluster_block<TRA>"};
-    static const char* const nm_g[4] = {"k_cluster_giant<INDEL>", "k_cluster_giant<DUP>", "k_cluster_giant<INV>", "k_cluster_giant<TRA>"};
     LAUNCH_NAMED(c, nm_w[KIND], (k_cluster_warp<KIND>), c->n_sm * 3, CL_THREADS, smem_warp, J, E, ctr, work);
-    LAUNCH_NAMED(c, nm_b[KIND], (k_cluster_block<false, KIND>), c->n_sm, CL_THREADS, (size_t)BLOCK_M * ARENA_PER_MAX, J, E, ctr);
-    LAUNCH_NAMED(c, nm_g[KIND], (k_cluster_block<true, KIND>), c->n_sm, CL_THREADS, 0, J, E, ctr);
+    LAUNCH_NAMED(c, nm_b[KIND], (k_cluster_block<KIND>), c->n_sm, CL_THREADS, (size_t)BLOCK_M * ARENA_PER_MAX, J, E, ctr);
 }
 
 static int grid_for(const csv_ctx* c, int64_t n, int block, int per_sm = 8) {
@@ -396,10 +397,10 @@ extern "C" int csv_create(int device, void* stream, csv_ctx** out) {
     CU(cudaFuncSetAttribute(k_cluster_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
     CU(cudaFuncSetAttribute(k_cluster_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
     CU(cudaFuncSetAttribute(k_cluster_warp<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
-    CU(cudaFuncSetAttribute((k_cluster_block<false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
-    CU(cudaFuncSetAttribute((k_cluster_block<false, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
-    CU(cudaFuncSetAttribute((k_cluster_block<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
-    CU(cudaFuncSetAttribute((k_cluster_block<false, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
+    CU(cudaFuncSetAttribute(k_cluster_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
+    CU(cudaFuncSetAttribute(k_cluster_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
+    CU(cudaFuncSetAttribute(k_cluster_block<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
+    CU(cudaFuncSetAttribute(k_cluster_block<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
     *out = c;
     return CSV_OK;
 }
@@ -415,7 +416,7 @@ extern "C" int csv_destroy(csv_ctx* c) {
                    &c->small.perm_a, &c->small.perm_b, &c->small.sel, &c->small.u_chrom, &c->small.u_a, &c->small.u_b,
                    &c->small.u_rid, &c->small.u_c, &c->boff, &c->rec_a, &c->rec_b, &c->recc_a, &c->recc_b, &c->big_bkt, &c->d_epoch,
                    &c->d_len_eff, &c->g_send, &c->g_recv, &c->g_cand, &c->g_geno, &c->g_names, &c->g_scratch, &c->cal_in0, &c->cal_in1,
-                   &c->cal_out, &c->aln_flag, &c->scan_carry};
+                   &c->cal_out, &c->aln_flag, &c->scan_carry, &c->win_rec};
     for (DBuf* b : all) b->release();
     for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->comm) comm_destroy(c);
@@ -834,7 +835,9 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
         BigBuckets BB{c->big_bkt.as<uint4>(), bb_cap, c->tickets.as<uint32_t>() + c->ticket_next++};
         {
             const int g = (int)std::min<uint32_t>(n_tiles, (uint32_t)c->n_sm * 8);
-#define BP_LAUNCH(RB) LAUNCH(c, (k_bucket_prefix<RB>), g, 256, 0, c->bkt.as<uint32_t>(), n_buckets, rb, (uint32_t)J.cp.min_support, bpre, tile_base, BB, &ctr->status)
+            if (c->ticket_next >= (int)LB_ORDINALS) return set_err(CSV_E_STATE, "ticket pool exhausted");
+            uint32_t* done_ctr = c->tickets.as<uint32_t>() + c->ticket_next++;
+#define BP_LAUNCH(RB) LAUNCH(c, (k_bucket_prefix<RB>), g, 256, 0, c->bkt.as<uint32_t>(), n_buckets, rb, (uint32_t)J.cp.min_support, bpre, tile_base, BB, &ctr->status, done_ctr, n_pass)
             switch (rb) {
                 case 1: BP_LAUNCH(1); break; case 2: BP_LAUNCH(2); break; case 3: BP_LAUNCH(3); break; case 4: BP_LAUNCH(4); break;
                 case 5: BP_LAUNCH(5); break; case 6: BP_LAUNCH(6); break; case 7: BP_LAUNCH(7); break; case 8: BP_LAUNCH(8); break;
@@ -842,16 +845,13 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
             }
 #undef BP_LAUNCH
         }
-        LAUNCH(c, k_scan_small, 1, 1024, 0, tile_base, (int64_t)n_tiles, n_pass);
         uint2* pairs = (uint2*)c->keys_a.p;   // 8 B per signature (ensure_lane_scratch)
         LAUNCH(c, k_indel_scatter, grid_for(c, n, 256 * 4), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), n, t == CSV_INS ? 1 : 0, ct,
                (const uint32_t*)bpre, (const uint32_t*)tile_base, c->bkt.as<uint32_t>(), pairs);
         stage_end(c, CSV_ST_KEYS);
         stage_begin(c, CSV_ST_SORT);
         LAUNCH(c, k_bucket_fixup, grid_for(c, n, FX_TILE, 8), 256, 0, (const uint2*)pairs, n_pass, c->keys_b.as<uint32_t>(),
-               c->vals_b.as<uint32_t>(), c->bkt.as<uint32_t>(), (int64_t)n_bkt);
-        LAUNCH(c, k_bucket_fixup_big, c->n_sm, 256, 0, (const uint2*)pairs, BB, (const uint32_t*)tile_base, c->keys_b.as<uint32_t>(),
-               c->vals_b.as<uint32_t>());
+               c->vals_b.as<uint32_t>(), c->bkt.as<uint32_t>(), (int64_t)n_bkt, BB, (const uint32_t*)tile_base);
         stage_end(c, CSV_ST_SORT);
         J.n_dev = n_pass;
         J.keys32 = c->keys_b.as<uint32_t>();
@@ -1058,6 +1058,7 @@ static int ensure_workspace(csv_ctx* c, uint32_t type_mask) {
     CU(c->names.ensure((size_t)c->cap_names * 4));
     CU(c->dr.ensure((size_t)c->cap_cand * 4));
     CU(c->win_list.ensure((size_t)c->cap_cand * 2 * 4));
+    CU(c->win_rec.ensure((size_t)c->cap_cand * 2 * sizeof(WinRec)));
     CU(c->has_rows.ensure((size_t)c->n_contigs + 16));
     return CSV_OK;
 }
@@ -1080,10 +1081,10 @@ static int enqueue_cluster(csv_ctx* c, uint32_t type_mask) {
     stage_reset_if_consumed(c);
     c->last_mask = type_mask;
     c->ticket_next = 0;
-    LAUNCH(c, k_epoch_bump, 1, 32, 0, c->d_epoch.as<uint32_t>());   // fresh look-back generation for every launch of this call
-    CU(cudaMemsetAsync(c->tickets.p, 0, LB_ORDINALS * 4, c->stream));
-    CU(cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), c->stream));
-    CU(cudaMemsetAsync(c->cnt.p, 0, c->cnt.cap, c->stream));
+    // fresh look-back generation, zeroed tickets and counters.  (The per-cluster row counts `cnt` need no clearing: every
+    // kept-cluster slot below n_kept[t] is written by a cluster kernel and the order scans stop at n_kept[t].)
+    LAUNCH(c, k_begin, 1, 256, 0, c->d_epoch.as<uint32_t>(), c->tickets.as<uint32_t>(), (int)LB_ORDINALS, c->counters.as<uint32_t>(),
+           (int)(sizeof(Counters) / 4));
     Counters* ctr = c->counters.as<Counters>();
     uint32_t kslot_base = 0;
     // fork: every lane's chain starts after the resets above; join before `order`
@@ -1128,6 +1129,21 @@ static int enqueue_cluster(csv_ctx* c, uint32_t type_mask) {
     rc = join_lanes(c);
     if (rc) return rc;
     if (aux_used) CU(cudaStreamWaitEvent(c->stream, c->ev_aux, 0));
+    GenoJob G;
+    memset(&G, 0, sizeof(G));
+    G.cand = c->cand.as<csv_cand>(); G.geno = c->geno.as<csv_geno>(); G.names = c->names.as<int32_t>(); G.ctr = ctr;
+    G.cap_cand = c->cap_cand;
+    G.ct = ContigTab{c->d_off.as<uint64_t>(), c->d_len_eff.as<int64_t>(), c->n_contigs};
+    G.gp = GtParams{c->P.bias_del, c->P.gt_bias_ins, c->P.bias_dup, c->P.bias_inv};
+    G.shift = geno_shift;
+    G.n_bins = geno_bins;
+    G.bin_start = c->bin_start.as<uint32_t>(); G.bin_fill = c->bin_fill.as<uint32_t>(); G.bin_bits = c->bin_bits.as<uint32_t>();
+    G.win_list = c->win_list.as<uint32_t>(); G.win_cap = c->cap_cand * 2;
+    G.lin32 = (total_len + 4096) < (1ull << 32) ? 1 : 0;   // (window ends may pass the last contig by a bias)
+    G.win_rec = c->win_rec.as<WinRec>();
+    G.dr = c->dr.as<uint32_t>(); G.has_rows = c->has_rows.as<uint8_t>();
+    G.gl_table = c->gl_table.as<csv_geno>();
+    G.genotype = c->P.genotype;
     // ---- order ----
     stage_begin(c, CSV_ST_ORDER);
     {
@@ -1148,8 +1164,9 @@ static int enqueue_cluster(csv_ctx* c, uint32_t type_mask) {
             kb += c->kept_cap[t];
             prev = t;
         }
+        // final order; the same pass counts the genotype windows per bin
         LAUNCH(c, k_permute, grid_for(c, c->cap_cand, 256, 4), 256, 0, c->cand_tmp.as<csv_cand>(), c->cnt.as<uint32_t>(), ctr, c->cap_cand,
-               c->cand.as<csv_cand>());
+               c->cand.as<csv_cand>(), G);
     }
     stage_end(c, CSV_ST_ORDER);
     // ---- genotype ----
@@ -1157,21 +1174,7 @@ static int enqueue_cluster(csv_ctx* c, uint32_t type_mask) {
     if (rc) return rc;
     stage_begin(c, CSV_ST_GENOTYPE);
     {
-        GenoJob G;
-        memset(&G, 0, sizeof(G));
-        G.cand = c->cand.as<csv_cand>(); G.geno = c->geno.as<csv_geno>(); G.names = c->names.as<int32_t>(); G.ctr = ctr;
-        G.cap_cand = c->cap_cand;
-        G.ct = ContigTab{c->d_off.as<uint64_t>(), c->d_len_eff.as<int64_t>(), c->n_contigs};
-        G.gp = GtParams{c->P.bias_del, c->P.gt_bias_ins, c->P.bias_dup, c->P.bias_inv};
-        G.shift = geno_shift;
-        G.n_bins = geno_bins;
-        G.bin_start = c->bin_start.as<uint32_t>(); G.bin_fill = c->bin_fill.as<uint32_t>(); G.bin_bits = c->bin_bits.as<uint32_t>();
-        G.win_list = c->win_list.as<uint32_t>(); G.win_cap = c->cap_cand * 2;
-        G.dr = c->dr.as<uint32_t>(); G.has_rows = c->has_rows.as<uint8_t>();
-        G.gl_table = c->gl_table.as<csv_geno>();
-        G.genotype = c->P.genotype;
         if (c->P.genotype) {
-            LAUNCH(c, (k_windows<0>), grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
             TileSync ts;
             rc = make_sync(c, (size_t)((G.n_bins + 1) / SEL_TILE + 2), &ts);
             if (rc) return rc;
@@ -1182,13 +1185,21 @@ static int enqueue_cluster(csv_ctx* c, uint32_t type_mask) {
                 PairBuf PB;
                 PB.cap = (uint32_t)std::min<int64_t>(4 * c->n_reads + (1 << 20), (int64_t)1 << 30);
                 if (c->pair_cap_override > 0) PB.cap = (uint32_t)c->pair_cap_override;  // tests: force the overflow path
-                CU(c->pairs.ensure((size_t)PB.cap * sizeof(uint2)));
+                CU(c->pairs.ensure((size_t)PB.cap * (G.lin32 ? sizeof(uint4) : sizeof(uint2))));
                 PB.pairs = c->pairs.as<uint2>();
+                PB.pairs4 = c->pairs.as<uint4>();
                 PB.count = &ctr->n_windows;
-                LAUNCH(c, k_reads_pass, grid_for(c, c->n_reads, 1024, 8), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
-                       c->r_end.as<int32_t>(), c->r_id.as<int32_t>(), c->r_prim.as<uint8_t>(), c->n_reads, &ctr->status);
-                LAUNCH(c, k_pairs_test, c->n_sm * 8, 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
-                       c->r_end.as<int32_t>(), c->r_id.as<int32_t>());
+                if (G.lin32) {
+                    LAUNCH(c, (k_reads_pass<true>), grid_for(c, c->n_reads, 1024, 8), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                           c->r_end.as<int32_t>(), c->r_id.as<int32_t>(), c->r_prim.as<uint8_t>(), c->n_reads, &ctr->status);
+                    LAUNCH(c, (k_pairs_test<true>), c->n_sm * 8, 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                           c->r_end.as<int32_t>(), c->r_id.as<int32_t>());
+                } else {
+                    LAUNCH(c, (k_reads_pass<false>), grid_for(c, c->n_reads, 1024, 8), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                           c->r_end.as<int32_t>(), c->r_id.as<int32_t>(), c->r_prim.as<uint8_t>(), c->n_reads, &ctr->status);
+                    LAUNCH(c, (k_pairs_test<false>), c->n_sm * 8, 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                           c->r_end.as<int32_t>(), c->r_id.as<int32_t>());
+                }
             }
         }
         LAUNCH(c, k_finalize, grid_for(c, c->cap_cand, 256, 4), 256, 0, G);

@@ -119,7 +119,13 @@ struct TileSync {
     uint32_t ordinal;        // unique per look-back launch inside one call (< LB_ORDINALS)
 };
 static constexpr uint32_t LB_ORDINALS = 1024;
-__global__ void k_epoch_bump(uint32_t* epoch) { if (threadIdx.x == 0) *epoch += 1u; }
+// first node of every csv_cluster call: fresh look-back generation, zeroed ticket words and counters (one launch
+// instead of a kernel and two memsets)
+__global__ void __launch_bounds__(256) k_begin(uint32_t* epoch, uint32_t* tickets, int n_tickets, uint32_t* counters, int n_counters) {
+    if (threadIdx.x == 0) *epoch += 1u;
+    for (int i = threadIdx.x; i < n_tickets; i += 256) tickets[i] = 0u;
+    for (int i = threadIdx.x; i < n_counters; i += 256) counters[i] = 0u;
+}
 __device__ __forceinline__ uint32_t ts_gen(const TileSync& ts) { return (*ts.epoch) * LB_ORDINALS + ts.ordinal; }
 
 // Ordered select: out[k] = i for the k-th i in [0, n) with pred(i); *out_count = number selected.

@@ -52,6 +52,7 @@ struct ExtractOut {
     uint32_t* n_rows;
     uint32_t cap_rows;
     uint32_t* status;       // ST_* bits (overflow)
+    uint32_t* n_skipped;    // records whose split-read analysis was skipped (more than MAX_SEGS segments), may be null
 };
 
 CSV_HD int64_t emit_sig(const ExtractOut& O, int t, int32_t chrom, int32_t a, int32_t b, int32_t rid, int32_t c) {
@@ -90,7 +91,7 @@ struct MergeState {
     int del_open; int32_t del_pos, del_len, del_cmp;
     CSV_HD void reset() { ins_open = 0; del_open = 0; ins_pos = ins_len = ins_seqlen = ins_last = ins_np = 0; del_pos = del_len = del_cmp = 0; }
 };
-static constexpr int MAX_OPEN_PIECES = 64;  // pieces buffered per open merged INS (the rest are counted but dropped -> status)
+static constexpr int MAX_OPEN_PIECES = 64;  // pieces buffered per open merged INS; longer chains are rebuilt on the host (flush_ins)
 
 struct ReadCtx {
     int32_t rec, chrom, rid, qlen;
@@ -101,11 +102,15 @@ CSV_HD void flush_ins(const ExtractOut& O, const ReadCtx& R, MergeState& S, cons
     if (!S.ins_open) return;
     const int64_t k = emit_sig(O, CSV_INS, R.chrom, 2 * S.ins_pos, S.ins_len, R.rid, S.ins_seqlen);
     if (k >= 0) {
-        const int np = S.ins_np < MAX_OPEN_PIECES ? S.ins_np : MAX_OPEN_PIECES;
-        if (S.ins_np > MAX_OPEN_PIECES) atomic_or_u32(O.status, ST_INTERNAL);
+        // More merged insertions than the open-piece buffer holds (the reference has no limit, cuteSV:537-540): position, length
+        // and len(seq) of the signature are complete; its piece list becomes ONE marker piece (rc == 2, start = reference
+        // position of the merged group) from which the host rebuilds the string by walking that record's CIGAR again.
+        const bool spill = S.ins_np > MAX_OPEN_PIECES;
+        const int np = spill ? 1 : S.ins_np;
         const int64_t p = reserve_pieces(O, (uint32_t)np);
         if (p >= 0) {
-            for (int i = 0; i < np; i++) O.pieces[p + i] = open_pieces[i];
+            if (spill) { InsPiece mk; mk.rec = R.rec; mk.start = S.ins_pos; mk.stop = 0; mk.rc = 2; O.pieces[p] = mk; }
+            else for (int i = 0; i < np; i++) O.pieces[p + i] = open_pieces[i];
             O.ins_piece_off[k] = (int32_t)p; O.ins_piece_cnt[k] = np;
         } else { O.ins_piece_off[k] = 0; O.ins_piece_cnt[k] = 0; }
     }
@@ -352,7 +357,9 @@ CSV_HD void organize_split_signal(const SplitCtx& C, bool has_primary, const Seg
         }
     }
     if (total <= C.P.max_split_parts || C.P.max_split_parts == -1) {
-        if (total > MAX_SEGS) { atomic_or_u32(C.O->status, ST_INTERNAL); return; }
+        // only reachable with --max_split_parts -1: a record with more than MAX_SEGS qualifying segments is not analysed for
+        // split signatures (its CIGAR signatures are taken); reported, not fatal (ST_SKIPPED, ExtractOut::n_skipped)
+        if (total > MAX_SEGS) { atomic_or_u32(C.O->status, ST_SKIPPED); if (C.O->n_skipped) atomic_add_u32(C.O->n_skipped, 1u); return; }
         analysis_split_read(C, segs, n);
     }
 }

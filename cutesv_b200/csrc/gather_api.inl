@@ -119,60 +119,62 @@ __global__ void __launch_bounds__(256) k_gather_pack(const csv_cand* __restrict_
     for (int64_t i = tid; i < cn; i += stride) dst_n[i] = names[i];
 }
 
-// Merged order = the single-GPU order: svtype, contig id, then (rank, emission order).  With contig shards every
-// (svtype, contig) group comes from one rank; the (key, rank) counters make the merge well defined for any inputs.
+// Merged order = the single-GPU order: svtype, contig id, then (rank, emission order).  Every rank's records are already
+// in that order, so a record's merged position is a sum of binary searches: (records of every rank with a smaller key)
+// + (records of lower ranks with the same key) + its offset inside its own key group.  ONE kernel, no scratch: with
+// contig shards every (svtype, contig) group comes from one rank, but the rule is well defined for any inputs.
 struct MergeJob {
     const char* recv; GatherLayout L; int world; int32_t n_contigs;
-    uint32_t* cnt;     // [n_keys * world] counts, then exclusive offsets
-    uint32_t* first;   // [n_keys * world] index (inside its rank) of the first record of the group
-    csv_cand* out_c; csv_geno* out_g; int32_t* out_n; int64_t cap_c, cap_n; uint32_t* status;
+    csv_cand* out_c; csv_geno* out_g; int32_t* out_n; int64_t cap_c, cap_n;
+    int64_t* hdr;   // [world * GH_WORDS + 1]: compact copy of the headers + a status word (one D2H copy)
 };
 __device__ __forceinline__ const int64_t* gm_header(const MergeJob& M, int r) { return (const int64_t*)(M.recv + (int64_t)r * M.L.msg_bytes); }
 __device__ __forceinline__ int64_t gm_valid(const MergeJob& M, int r) {
     const int64_t n = gm_header(M, r)[0];
     return n < M.L.pad_cand ? n : M.L.pad_cand;
 }
-__global__ void __launch_bounds__(256) k_gm_count(MergeJob M) {
-    const int64_t per = M.L.pad_cand, total = per * M.world;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        const int r = (int)(g / per);
-        const int64_t i = g - (int64_t)r * per;
-        if (i >= gm_valid(M, r)) continue;
-        const csv_cand* cs = (const csv_cand*)(M.recv + (int64_t)r * M.L.msg_bytes + GH_WORDS * 8);
-        const int32_t sv = cs[i].svtype, ch = cs[i].chrom;
-        if (sv < 0 || sv >= CSV_NTYPES || ch < 0 || ch >= M.n_contigs) { atomicOr(M.status, 1u); continue; }
-        const int64_t slot = ((int64_t)sv * M.n_contigs + ch) * M.world + r;
-        if (i == 0 || cs[i - 1].svtype != sv || cs[i - 1].chrom != ch) M.first[slot] = (uint32_t)i;
-        atomicAdd(&M.cnt[slot], 1u);
+__device__ __forceinline__ int64_t gm_key(const csv_cand& c) { return ((int64_t)c.svtype << 32) | (uint32_t)c.chrom; }
+// number of records of rank r with key < k (UPPER: <= k)
+template <bool UPPER>
+__device__ __forceinline__ int64_t gm_bound(const MergeJob& M, int r, int64_t k) {
+    const csv_cand* cs = (const csv_cand*)(M.recv + (int64_t)r * M.L.msg_bytes + GH_WORDS * 8);
+    int64_t lo = 0, hi = gm_valid(M, r);
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const int64_t km = ((int64_t)cs[mid].svtype << 32) | (uint32_t)cs[mid].chrom;
+        if (UPPER ? km <= k : km < k) lo = mid + 1; else hi = mid;
     }
+    return lo;
 }
-__global__ void __launch_bounds__(256) k_gm_place(MergeJob M) {
+__global__ void __launch_bounds__(256) k_gather_merge(MergeJob M) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if (tid < (int64_t)M.world * GH_WORDS) M.hdr[tid] = gm_header(M, (int)(tid / GH_WORDS))[tid % GH_WORDS];
     const int64_t per = M.L.pad_cand, total = per * M.world;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t g = tid; g < total; g += stride) {
         const int r = (int)(g / per);
         const int64_t i = g - (int64_t)r * per;
         if (i >= gm_valid(M, r)) continue;
         const char* msg = M.recv + (int64_t)r * M.L.msg_bytes;
-        const csv_cand* cs = (const csv_cand*)(msg + GH_WORDS * 8);
-        csv_cand c = cs[i];
-        if (c.svtype < 0 || c.svtype >= CSV_NTYPES || c.chrom < 0 || c.chrom >= M.n_contigs) continue;
-        const int64_t slot = ((int64_t)c.svtype * M.n_contigs + c.chrom) * M.world + r;
-        const int64_t dst = (int64_t)M.cnt[slot] + (i - (int64_t)M.first[slot]);
-        int64_t nbase = 0;
+        csv_cand c = ((const csv_cand*)(msg + GH_WORDS * 8))[i];
+        if (c.svtype < 0 || c.svtype >= CSV_NTYPES || c.chrom < 0 || c.chrom >= M.n_contigs) { M.hdr[M.world * GH_WORDS] = 1; continue; }
+        const int64_t k = gm_key(c);
+        int64_t dst = i, nbase = 0;   // i = (records of rank r with a smaller key) + offset inside the own group
+        for (int q = 0; q < M.world; q++) {
+            if (q == r) continue;
+            dst += q < r ? gm_bound<true>(M, q, k) : gm_bound<false>(M, q, k);
+        }
         for (int q = 0; q < r; q++) nbase += gm_header(M, q)[1];
         c.names_off += (int32_t)nbase;
         c.reserved[1] = r;   // source rank: csv_cand.aux of an INS row indexes THAT rank's INS signature array
         if (dst < M.cap_c) { M.out_c[dst] = c; M.out_g[dst] = ((const csv_geno*)(msg + M.L.off_geno))[i]; }
-        else atomicOr(M.status, 2u);
+        else M.hdr[M.world * GH_WORDS] = 2;
     }
-}
-__global__ void __launch_bounds__(256) k_gm_names(MergeJob M) {
     int64_t nbase = 0;
     for (int r = 0; r < M.world; r++) {
         const int64_t nn = gm_header(M, r)[1];
         const int64_t cn = nn < M.L.pad_names ? nn : M.L.pad_names;
         const int32_t* src = (const int32_t*)(M.recv + (int64_t)r * M.L.msg_bytes + M.L.off_names);
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cn; i += (int64_t)gridDim.x * blockDim.x)
+        for (int64_t i = tid; i < cn; i += stride)
             if (nbase + i < M.cap_n) M.out_n[nbase + i] = src[i];
         nbase += nn;
     }
@@ -183,29 +185,21 @@ static int gather_enqueue(csv_ctx* c) {
     const int W = c->world;
     CU(c->g_send.ensure((size_t)L.msg_bytes));
     CU(c->g_recv.ensure((size_t)L.msg_bytes * W));
-    const int64_t n_keys = (int64_t)CSV_NTYPES * c->n_contigs * W;
-    CU(c->g_scratch.ensure((size_t)n_keys * 8 + 64));
+    CU(c->g_scratch.ensure((size_t)(W * GH_WORDS + 8) * 8, true));   // compact headers + status word (zero when allocated)
     CU(c->g_cand.ensure((size_t)L.pad_cand * W * sizeof(csv_cand) + 64));
     CU(c->g_geno.ensure((size_t)L.pad_cand * W * sizeof(csv_geno) + 64));
     CU(c->g_names.ensure((size_t)L.pad_names * W * 4 + 64));
+    // pack -> ONE ncclAllGather -> merge: three launches and one small D2H copy per step
     LAUNCH(c, k_gather_pack, c->n_sm * 2, 256, 0, c->cand.as<csv_cand>(), c->geno.as<csv_geno>(), c->names.as<int32_t>(),
            c->counters.as<Counters>(), c->cap_cand, c->cap_names, L, c->rank, c->g_send.as<char>());
     NC(g_nccl.AllGather(c->g_send.p, c->g_recv.p, (size_t)L.msg_bytes, ncclUint8, c->comm, c->stream));
-    CU(cudaMemsetAsync(c->g_scratch.p, 0, (size_t)n_keys * 8 + 64, c->stream));
     MergeJob M;
     M.recv = c->g_recv.as<char>(); M.L = L; M.world = W; M.n_contigs = c->n_contigs;
-    M.cnt = c->g_scratch.as<uint32_t>(); M.first = M.cnt + n_keys; M.status = M.first + n_keys;
     M.out_c = c->g_cand.as<csv_cand>(); M.out_g = c->g_geno.as<csv_geno>(); M.out_n = c->g_names.as<int32_t>();
     M.cap_c = L.pad_cand * W; M.cap_n = L.pad_names * W;
-    const int grid = grid_for(c, L.pad_cand * W, 256, 4);
-    LAUNCH(c, k_gm_count, grid, 256, 0, M);
-    LAUNCH(c, k_scan_small, 1, 1024, 0, M.cnt, n_keys, (uint32_t*)nullptr);
-    LAUNCH(c, k_gm_place, grid, 256, 0, M);
-    LAUNCH(c, k_gm_names, grid_for(c, L.pad_names, 256, 2), 256, 0, M);
-    // headers of all ranks (+ the merge status word) for csv_gathered_counts
-    for (int r = 0; r < W; r++)
-        CU(cudaMemcpyAsync(c->h_gather + 4 * r, c->g_recv.as<char>() + (size_t)r * L.msg_bytes, GH_WORDS * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(c->h_gather + 4 * W, M.status, 4, cudaMemcpyDeviceToHost, c->stream));
+    M.hdr = c->g_scratch.as<int64_t>();
+    LAUNCH(c, k_gather_merge, grid_for(c, std::max<int64_t>(L.pad_cand * W, L.pad_names), 256, 4), 256, 0, M);
+    CU(cudaMemcpyAsync(c->h_gather, M.hdr, (size_t)(W * GH_WORDS + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     c->gathered = true;
     return CSV_OK;
 }
@@ -226,7 +220,7 @@ extern "C" int csv_allgather(csv_ctx* c) {
         int64_t nc = 0, nn = 0;
         int rc = csv_result_counts(c, &nc, &nn);
         if (rc) return rc;
-        CU(c->g_scratch.ensure(64));
+        CU(c->g_scratch.ensure((size_t)(c->world * GH_WORDS + 8) * 8, true));
         int64_t h[2] = {nc, nn};
         CU(cudaMemcpyAsync(c->g_scratch.p, h, 16, cudaMemcpyHostToDevice, c->stream));
         NC(g_nccl.AllReduce(c->g_scratch.p, c->g_scratch.p, 2, ncclInt64, ncclMax, c->comm, c->stream));
@@ -257,7 +251,10 @@ extern "C" int csv_gathered_counts(csv_ctx* c, int64_t* n_cand, int64_t* n_names
             mc = std::max(mc, h[0]); mn = std::max(mn, h[1]);
         }
         if (!over) {
-            if ((uint32_t)c->h_gather[4 * c->world] != 0) return set_err(CSV_E_CUDA, "csv_allgather: merge failed (status %u)", (uint32_t)c->h_gather[4 * c->world]);
+            if (c->h_gather[4 * c->world] != 0) {
+                cudaMemsetAsync(c->g_scratch.as<int64_t>() + 4 * c->world, 0, 8, c->stream);
+                return set_err(CSV_E_CUDA, "csv_allgather: merge failed (status %lld)", (long long)c->h_gather[4 * c->world]);
+            }
             c->g_n_cand = tc; c->g_n_names = tn;
             if (n_cand) *n_cand = tc;
             if (n_names) *n_names = tn;

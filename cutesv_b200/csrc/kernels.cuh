@@ -424,9 +424,10 @@ struct BigBuckets { uint4* list; uint32_t cap; uint32_t* count; };   // (tile, o
 template <int RB>
 __global__ void __launch_bounds__(256) k_bucket_prefix(const uint32_t* __restrict__ bkt, uint32_t n_buckets, int rb, uint32_t need,
                                                        uint32_t* __restrict__ bpre, uint32_t* __restrict__ tile_tot, BigBuckets BB,
-                                                       uint32_t* status) {
+                                                       uint32_t* status, uint32_t* done_ctr, uint32_t* n_out) {
     __shared__ uint32_t s_b[RB == 0 ? (BP_TILE + 2 * BKT_PAD + 8) * 17 / 16 + 8 : 1];
     __shared__ uint32_t s_warp[9];
+    __shared__ uint32_t s_last;
     auto P = [](int i) { return i + (i >> 4); };   // +1 word per 16: threads stride 17 words -> no bank conflicts
     const uint32_t n_tiles = (n_buckets + BP_TILE - 1) / BP_TILE;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -483,6 +484,23 @@ __global__ void __launch_bounds__(256) k_bucket_prefix(const uint32_t* __restric
         for (int j = 0; j < BP_PER; j += 4) dst[j >> 2] = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         if (RB == 0) __syncthreads();
     }
+    // the CTA that finishes last turns the tile totals into tile bases (a few thousand words) and reports the number of
+    // survivors: no separate scan launch
+    __threadfence();
+    if (threadIdx.x == 0) s_last = atomicAdd(done_ctr, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_tiles; base += 256) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_tiles ? __ldcg(&tile_tot[i]) : 0u;
+        uint32_t total;
+        const uint32_t ex = block_excl_scan_256(v, s_warp, &total);
+        if (i < n_tiles) tile_tot[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *n_out = carry;
 }
 
 // exclusive scan of arr[0..n) by ONE CTA (n: a few thousand words), *total_out = sum
@@ -556,8 +574,10 @@ __global__ void __launch_bounds__(256) k_indel_scatter(const int32_t* __restrict
 // the bucket histogram is cleared for the next call (flagged buckets were counted down to zero, the others not).
 static constexpr int FX_TILE = 2048;
 __global__ void __launch_bounds__(256) k_bucket_fixup(const uint2* __restrict__ pairs, const uint32_t* n_dev, uint32_t* __restrict__ keys_out,
-                                                      uint32_t* __restrict__ idx_out, uint32_t* __restrict__ bkt, int64_t n_bkt) {
+                                                      uint32_t* __restrict__ idx_out, uint32_t* __restrict__ bkt, int64_t n_bkt, BigBuckets BB,
+                                                      const uint32_t* __restrict__ tile_base) {
     __shared__ uint32_t s_k[FX_TILE + 2 * FIX_SMALL];
+    __shared__ uint32_t s_warp[9];
     {
         uint4* b4 = reinterpret_cast<uint4*>(bkt);   // n_bkt is a multiple of 4, cudaMalloc alignment
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -602,14 +622,10 @@ __global__ void __launch_bounds__(256) k_bucket_fixup(const uint2* __restrict__ 
         }
         __syncthreads();
     }
-}
-// big buckets (pile-ups): one CTA per bucket, counting sort on the low BKT_SHIFT bits of the key
-__global__ void __launch_bounds__(256) k_bucket_fixup_big(const uint2* __restrict__ pairs, BigBuckets BB, const uint32_t* __restrict__ tile_base,
-                                                          uint32_t* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
+    // big buckets (pile-ups, listed by k_bucket_prefix): one CTA per bucket, counting sort on the low BKT_SHIFT bits
     constexpr int NB = 1 << BKT_SHIFT;
     static_assert(NB == 256, "one histogram bin per thread");
-    __shared__ uint32_t s_cnt[NB];
-    __shared__ uint32_t s_warp[9];
+    uint32_t* s_cnt = s_k;
     const uint32_t n_list = min(*BB.count, BB.cap);
     for (uint32_t q = blockIdx.x; q < n_list; q += gridDim.x) {
         const uint4 e = BB.list[q];
@@ -631,7 +647,6 @@ __global__ void __launch_bounds__(256) k_bucket_fixup_big(const uint2* __restric
         __syncthreads();
     }
 }
-
 // small types: three sort keys per signature (name, second coordinate, primary)
 __global__ void k_other_keys(const int32_t* __restrict__ chrom, const int32_t* __restrict__ a, const int32_t* __restrict__ b,
                              const int32_t* __restrict__ rid, const int32_t* __restrict__ c, int64_t n, int svtype, ContigTab ct,
@@ -790,31 +805,26 @@ __device__ __forceinline__ int64_t cluster_size_block(const TypeJob& J, int64_t 
     }
 }
 
-// one CTA per deferred cluster; GIANT = arena in global scratch instead of shared memory
-template <bool GIANT, int KIND>
+// one CTA per deferred cluster; clusters beyond the shared-memory arena (> BLOCK_M members) use global scratch
+template <int KIND>
 __global__ void __launch_bounds__(CL_THREADS) k_cluster_block(TypeJob J, Emit E, Counters* ctr) {
     extern __shared__ __align__(16) char smem[];
     __shared__ int64_t red[CL_THREADS + 8];
     const int64_t n = job_n(J);
-    const uint32_t n_list = GIANT ? min(ctr->n_giant[J.svtype], J.giant_cap) : min(ctr->n_big[J.svtype], J.big_cap);
-    const uint32_t* list = GIANT ? J.giant_list : J.big_list;
+    const uint32_t n_list = min(ctr->n_big[J.svtype], J.big_cap);
     CudaTeam<CL_THREADS> tm;
     for (uint32_t q = blockIdx.x; q < n_list; q += gridDim.x) {
-        const uint32_t k = list[q];
+        const uint32_t k = J.big_list[q];
         const int64_t s = J.kept_start[k];
         const int64_t m = cluster_size_block(J, s, n, red);
-        if (!GIANT && m > BLOCK_M) {
-            if (threadIdx.x == 0) {
-                const uint32_t o = atomicAdd(&ctr->n_giant[J.svtype], 1u);
-                if (o < J.giant_cap) J.giant_list[o] = k; else atomicOr(&ctr->status, ST_LIST_OVERFLOW);
-            }
-            __syncthreads();
-            continue;
-        }
+        const bool giant = m > BLOCK_M;
         const int M = pow2ceil((int)m);
-        if (threadIdx.x == 0) atomicAdd(&ctr->n_members[J.svtype], (uint32_t)m);
+        if (threadIdx.x == 0) {
+            atomicAdd(&ctr->n_members[J.svtype], (uint32_t)m);
+            if (giant) atomicAdd(&ctr->n_giant[J.svtype], 1u);
+        }
         // global scratch: clusters are disjoint ranges of the sorted order and M <= 2m
-        char* arena = GIANT ? (J.giant_arena + (size_t)(2 * s) * ARENA_PER_MAX) : smem;
+        char* arena = giant ? (J.giant_arena + (size_t)(2 * s) * ARENA_PER_MAX) : smem;
         run_cluster<KIND>(tm, J, s, (int)m, M, arena, red, J.kslot_base + k, E);
         __syncthreads();
     }
@@ -823,20 +833,12 @@ __global__ void __launch_bounds__(CL_THREADS) k_cluster_block(TypeJob J, Emit E,
 // ------------------------------------------------------------------------------------------
 // order: final position = (exclusive scan of per-cluster counts)[kslot] + emission rank
 // ------------------------------------------------------------------------------------------
-__global__ void k_permute(const csv_cand* __restrict__ tmp, const uint32_t* __restrict__ base, const Counters* ctr, uint32_t cap,
-                          csv_cand* __restrict__ out) {
-    const uint32_t n = min(ctr->n_cand, cap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        csv_cand c = tmp[i];
-        const uint32_t dst = base[c.cluster] + (uint32_t)c.reserved[0];
-        c.reserved[0] = 0;
-        if (dst < cap) out[dst] = c;
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // genotype
 // ------------------------------------------------------------------------------------------
+// One genotype window, ready to be tested against a read: linear bounds of this window and (second window of DUP / INV
+// only) of the candidate's first window, the slice of supporting read ids, the candidate index.  32 B = one sector.
+struct alignas(16) WinRec { uint32_t S, E, S0, E0; int32_t names_off, names_cnt; uint32_t cand, second; };
 struct GenoJob {
     csv_cand* cand;           // final order
     csv_geno* geno;
@@ -852,6 +854,8 @@ struct GenoJob {
     uint32_t* bin_bits;       // n_bins/32 + 1: bin holds at least one window (small, stays in L1)
     uint32_t* win_list;       // cand*2 + which, grouped by bin
     uint32_t win_cap;
+    struct WinRec* win_rec;   // lin32 only: the same slots as 32 B records (window bounds in linear coordinates, names slice, cand)
+    int lin32;                // the linear coordinate fits 32 bits: (read, window) pairs carry the read's coordinates
     uint32_t* dr;             // per candidate
     uint8_t* has_rows;        // per contig: reads table has rows (call_gt's `chr not in sigs_index["reads"]`)
     const csv_geno* gl_table;
@@ -864,7 +868,30 @@ __device__ __forceinline__ uint32_t window_bin(const GenoJob& G, const csv_cand&
     return (uint32_t)((G.ct.off[c.chrom] + (uint64_t)s) >> G.shift);
 }
 
-// pass 0: count windows per bin; pass 1: scatter them (bin_start already scanned)
+// candidates into the reference's emission order; when genotyping, the same pass counts the genotype windows per bin
+__global__ void k_permute(const csv_cand* __restrict__ tmp, const uint32_t* __restrict__ base, const Counters* ctr, uint32_t cap,
+                          csv_cand* __restrict__ out, GenoJob G) {
+    const uint32_t n = min(ctr->n_cand, cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        csv_cand c = tmp[i];
+        const uint32_t dst = base[c.cluster] + (uint32_t)c.reserved[0];
+        c.reserved[0] = 0;
+        if (dst >= cap) continue;
+        out[dst] = c;
+        if (G.genotype) {
+            const int nw = n_windows_of(c);
+            for (int w = 0; w < nw; w++) {
+                uint32_t b = window_bin(G, c, w);
+                if (b >= G.n_bins) b = G.n_bins - 1;
+                atomicAdd(&G.bin_start[b], 1u);
+                atomicOr(&G.bin_bits[b >> 5], 1u << (b & 31));
+            }
+            G.dr[dst] = 0;
+        }
+    }
+}
+
+// pass 1: scatter the windows into their bins (bin_start already scanned; pass 0 = the counting is part of k_permute)
 template <int PASS>
 __global__ void k_windows(GenoJob G) {
     const uint32_t n = min(G.ctr->n_cand, G.cap_cand);
@@ -877,7 +904,21 @@ __global__ void k_windows(GenoJob G) {
             if (PASS == 0) { atomicAdd(&G.bin_start[b], 1u); atomicOr(&G.bin_bits[b >> 5], 1u << (b & 31)); }
             else {
                 const uint32_t o = G.bin_start[b] + atomicAdd(&G.bin_fill[b], 1u);
-                if (o < G.win_cap) G.win_list[o] = i * 2u + (uint32_t)w;
+                if (o < G.win_cap) {
+                    G.win_list[o] = i * 2u + (uint32_t)w;
+                    if (G.lin32) {
+                        const uint64_t coff = G.ct.off[c.chrom];
+                        int64_t ws, we, s0 = 0, e0 = 0;
+                        window_of(c, w, G.gp, &ws, &we);
+                        if (w) window_of(c, 0, G.gp, &s0, &e0);
+                        WinRec r;
+                        r.S = (uint32_t)(coff + (uint64_t)ws); r.E = (uint32_t)(coff + (uint64_t)we);
+                        r.S0 = (uint32_t)(coff + (uint64_t)s0); r.E0 = (uint32_t)(coff + (uint64_t)e0);
+                        r.names_off = c.names_off; r.names_cnt = c.names_cnt; r.cand = i; r.second = (uint32_t)w;
+                        *reinterpret_cast<uint4*>(&G.win_rec[o]) = *reinterpret_cast<const uint4*>(&r);
+                        *(reinterpret_cast<uint4*>(&G.win_rec[o]) + 1) = *(reinterpret_cast<const uint4*>(&r) + 1);
+                    }
+                }
             }
         }
         if (PASS == 0) G.dr[i] = 0;
@@ -910,13 +951,32 @@ __device__ __forceinline__ void test_pair(const GenoJob& G, uint64_t RS, uint64_
     if (!found) atomicAdd(&G.dr[ent >> 1], 1u);
 }
 
+// the same test on a WinRec (32-bit linear coordinates): one 32 B gather instead of the candidate record, its contig
+// offset and the window arithmetic
+__device__ __forceinline__ void test_pair32(const GenoJob& G, uint32_t RS, uint32_t RE, int32_t rid, uint32_t w) {
+    const uint4 lo = __ldg(reinterpret_cast<const uint4*>(&G.win_rec[w])), hi = __ldg(reinterpret_cast<const uint4*>(&G.win_rec[w]) + 1);
+    if (!(RS <= lo.x && RE >= lo.y)) return;
+    if (hi.w && RS <= lo.z && RE >= lo.w) return;   // union of the two breakpoint covers (resolveDUP.py:155-157): count once
+    const int32_t* nm = G.names + (int32_t)hi.x;
+    const int n = (int32_t)hi.y;
+    bool found = false;
+    int k = 0;
+    for (; k + 4 <= n && !found; k += 4)
+        found = (__ldg(nm + k) == rid) | (__ldg(nm + k + 1) == rid) | (__ldg(nm + k + 2) == rid) | (__ldg(nm + k + 3) == rid);
+    for (; k < n && !found; k++) found = __ldg(nm + k) == rid;
+    if (!found) atomicAdd(&G.dr[hi.z], 1u);
+}
+
 // ONE streaming pass over the reads table (replaces overlap_cover's event sort + sweep,
 // cuteSV_genotype.py:95-159).  A read can only cover windows whose start lies in a bin it
 // overlaps; most reads overlap no occupied bin (bit test on an L1-resident map).  The few
 // (read, window) pairs that remain are compacted (warp-aggregated append) and tested by a second,
 // dense kernel so that the streaming pass keeps all 32 lanes busy.
-struct PairBuf { uint2* pairs; uint32_t cap; uint32_t* count; };
+// LIN32 (linear coordinate < 2^32): a pair is 16 B (read start, read end, read id, window slot), so the dense kernel
+// needs no gather into the reads table; otherwise 8 B (read row, window slot).
+struct PairBuf { uint2* pairs; uint4* pairs4; uint32_t cap; uint32_t* count; };
 
+template <bool LIN32>
 __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const int32_t* __restrict__ r_chrom,
                                                     const int32_t* __restrict__ r_start, const int32_t* __restrict__ r_end,
                                                     const int32_t* __restrict__ r_id, const uint8_t* __restrict__ r_prim,
@@ -935,9 +995,10 @@ __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const
             ch[j] = in ? r_chrom[r] : -1; st[j] = in ? r_start[r] : 0; en[j] = in ? r_end[r] : 0; pr[j] = in ? r_prim[r] : 0;
         }
         uint32_t w[ITEMS], cnt[ITEMS], total = 0;
+        uint64_t lin[ITEMS];   // RS of the read
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
-            w[j] = 0; cnt[j] = 0;
+            w[j] = 0; cnt[j] = 0; lin[j] = 0;
             const int64_t r = base + j * 256 + threadIdx.x;
             if (r >= n_reads) continue;
             if (ch[j] < 0 || ch[j] >= G.ct.n || G.ct.len[ch[j]] < 0) { atomicOr(status, ST_BAD_CHROM); continue; }   // len < 0: outside the shard
@@ -945,6 +1006,7 @@ __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const
             if (!pr[j]) continue;
             const uint64_t off = G.ct.off[ch[j]];
             const uint64_t RS = off + (uint64_t)(uint32_t)st[j], RE = off + (uint64_t)(uint32_t)en[j];
+            lin[j] = RS;
             const uint32_t b0 = (uint32_t)(RS >> G.shift);
             uint32_t b1 = (uint32_t)(RE >> G.shift);
             if (b1 >= G.n_bins) b1 = G.n_bins - 1;
@@ -963,29 +1025,38 @@ __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const
         for (int j = 0; j < ITEMS; j++) {
             if (!cnt[j]) continue;
             const int64_t r = base + j * 256 + threadIdx.x;
+            const int32_t rid = r_id[r];
+            const uint64_t RS = lin[j], RE = lin[j] + (uint64_t)(uint32_t)(en[j] - st[j]);
             // slots below the capacity go to the pair buffer (every reserved slot < cap MUST be written:
             // k_pairs_test consumes [0, min(count, cap))); the rest is tested inline (correct, just slower)
             uint32_t k = 0;
-            for (; k < cnt[j] && (uint64_t)o + k < PB.cap; k++) PB.pairs[o + k] = make_uint2((uint32_t)r, w[j] + k);
-            if (k < cnt[j]) {
-                const uint64_t off = G.ct.off[ch[j]];
-                const int32_t rid = r_id[r];
-                for (; k < cnt[j]; k++)
-                    test_pair(G, off + (uint64_t)(uint32_t)st[j], off + (uint64_t)(uint32_t)en[j], rid, w[j] + k);
+            for (; k < cnt[j] && (uint64_t)o + k < PB.cap; k++) {
+                if (LIN32) PB.pairs4[o + k] = make_uint4((uint32_t)RS, (uint32_t)RE, (uint32_t)rid, w[j] + k);
+                else PB.pairs[o + k] = make_uint2((uint32_t)r, w[j] + k);
+            }
+            for (; k < cnt[j]; k++) {
+                if (LIN32) test_pair32(G, (uint32_t)RS, (uint32_t)RE, rid, w[j] + k);
+                else test_pair(G, RS, RE, rid, w[j] + k);
             }
             o += cnt[j];
         }
     }
 }
 
+template <bool LIN32>
 __global__ void __launch_bounds__(256) k_pairs_test(GenoJob G, PairBuf PB, const int32_t* __restrict__ r_chrom,
                                                     const int32_t* __restrict__ r_start, const int32_t* __restrict__ r_end,
                                                     const int32_t* __restrict__ r_id) {
     const uint32_t n = min(*PB.count, PB.cap);
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        const uint2 pr = PB.pairs[p];
-        const uint64_t off = G.ct.off[r_chrom[pr.x]];
-        test_pair(G, off + (uint64_t)(uint32_t)r_start[pr.x], off + (uint64_t)(uint32_t)r_end[pr.x], r_id[pr.x], pr.y);
+        if (LIN32) {
+            const uint4 pr = PB.pairs4[p];
+            test_pair32(G, pr.x, pr.y, (int32_t)pr.z, pr.w);
+        } else {
+            const uint2 pr = PB.pairs[p];
+            const uint64_t off = G.ct.off[r_chrom[pr.x]];
+            test_pair(G, off + (uint64_t)(uint32_t)r_start[pr.x], off + (uint64_t)(uint32_t)r_end[pr.x], r_id[pr.x], pr.y);
+        }
     }
 }
 

@@ -272,9 +272,11 @@ def _pin_packet_method(self, packed):
     return out
 
 
-def _extract_method(self, packed):
+def _extract_method(self, packed, append=False):
     """csv_extract on a packing.pack_alignments() packet.  The extracted signatures and reads rows
-    stay device-resident as the inputs of cluster_device(); returns dict(counts, n_rows)."""
+    stay device-resident as the inputs of cluster_device(); returns dict(counts, n_rows).
+    append=True (csv_extract_append): this packet's output is appended to what earlier packets left on the device;
+    counts / n_rows are the totals so far and `first` holds the totals before this packet."""
     n = len(packed["chrom"])
     keep = [np.ascontiguousarray(packed[k], dtype=np.int32) for k in ("chrom", "ref_start", "ref_end", "flag", "mapq", "query_len", "read_id")]
     co = np.ascontiguousarray(packed["cigar_off"], dtype=np.int64)
@@ -285,11 +287,76 @@ def _extract_method(self, packed):
     cig = np.ascontiguousarray(packed["cigar"], dtype=np.uint32)
     counts = (C.c_int64 * _abi.CSV_NTYPES)()
     n_rows = C.c_int64(0)
-    _lib.check(self.L.csv_extract(self.h, C.byref(rc_), cig.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(len(cig)), C.byref(sa_), counts,
-                                  C.byref(n_rows)))
+    first = list(getattr(self, "_ex_counts", [0] * _abi.CSV_NTYPES)) if (append and getattr(self, "_ex_appending", False)) else [0] * _abi.CSV_NTYPES
+    first_rows = getattr(self, "_ex_rows", 0) if (append and getattr(self, "_ex_appending", False)) else 0
+    first_pieces = getattr(self, "_ex_pieces", 0) if (append and getattr(self, "_ex_appending", False)) else 0
+    fn = self.L.csv_extract_append if append else self.L.csv_extract
+    _lib.check(fn(self.h, C.byref(rc_), cig.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int64(len(cig)), C.byref(sa_), counts, C.byref(n_rows)))
     self._ex_counts = [int(x) for x in counts]
     self._ex_rows = int(n_rows.value)
-    return dict(counts={name: int(counts[t]) for t, name in enumerate(_abi.TYPE_NAMES)}, n_rows=int(n_rows.value))
+    self._ex_appending = bool(append)
+    npz = C.c_int64(0)
+    _lib.check(self.L.csv_fetch_pieces(self.h, C.c_int64(0), None, C.byref(npz)))
+    self._ex_pieces = int(npz.value)
+    return dict(counts={name: int(counts[t]) for t, name in enumerate(_abi.TYPE_NAMES)}, n_rows=int(n_rows.value),
+                first={name: first[t] for t, name in enumerate(_abi.TYPE_NAMES)}, first_rows=first_rows, first_pieces=first_pieces,
+                n_pieces=self._ex_pieces)
+
+
+def _extract_reset_method(self):
+    _lib.check(self.L.csv_extract_reset(self.h))
+    self._ex_counts = [0] * _abi.CSV_NTYPES
+    self._ex_rows = 0
+    self._ex_pieces = 0
+    self._ex_appending = False
+
+
+def _fetch_ins_pieces_method(self, first_sig, n_sig, first_piece, n_piece):
+    """Piece descriptors of INS signatures [first_sig, first_sig + n_sig) and pieces [first_piece, first_piece + n_piece):
+    what the host needs to rebuild the sequences of the rows ONE packet appended.  piece_off is re-based to the slice."""
+    po = np.zeros(max(n_sig, 1), dtype=np.int32)
+    pc = np.zeros(max(n_sig, 1), dtype=np.int32)
+    if n_sig:
+        _lib.check(self.L.csv_fetch_sigs_range(self.h, _abi.CSV_INS, C.c_int64(first_sig), C.c_int64(n_sig), None, None, None, None, None,
+                                               _abi.ptr(po), _abi.ptr(pc)))
+    pieces = np.zeros((max(n_piece, 1), 4), dtype=np.int32)
+    if n_piece:
+        _lib.check(self.L.csv_fetch_pieces_range(self.h, C.c_int64(first_piece), C.c_int64(n_piece), _abi.ptr(pieces)))
+    return po[:n_sig] - first_piece, pc[:n_sig], pieces[:n_piece]
+
+
+def _fetch_sig_cols_method(self, name, cols=("chrom", "a", "b", "read_id", "c")):
+    """D2H of whole columns of the device-resident signatures of one type."""
+    t = _abi.TYPE_IDS[name]
+    k = self._ex_counts[t]
+    out = {c: (np.zeros(max(k, 1), dtype=np.int32) if c in cols else None) for c in ("chrom", "a", "b", "read_id", "c")}
+    if k:
+        _lib.check(self.L.csv_fetch_sigs_range(self.h, t, C.c_int64(0), C.c_int64(k), *[(_abi.ptr(out[c]) if out[c] is not None else None)
+                                                                                          for c in ("chrom", "a", "b", "read_id", "c")], None, None))
+    return {c: (v[:k] if v is not None else None) for c, v in out.items()}
+
+
+def _fetch_read_rows_method(self):
+    """D2H of the device-resident reads table (reads_info_list rows, cuteSV:729-733)."""
+    nr = self._ex_rows
+    rows = {k: np.zeros(max(nr, 1), dtype=np.int32) for k in ("chrom", "start", "end", "read_id")}
+    prim = np.zeros(max(nr, 1), dtype=np.uint8)
+    _lib.check(self.L.csv_fetch_read_rows(self.h, C.c_int64(max(nr, 1)), _abi.ptr(rows["chrom"]), _abi.ptr(rows["start"]), _abi.ptr(rows["end"]),
+                                          _abi.ptr(rows["read_id"]), prim.ctypes.data_as(C.POINTER(C.c_uint8))))
+    rows = {k: v[:nr] for k, v in rows.items()}
+    rows["is_primary"] = prim[:nr]
+    return rows
+
+
+def _remap_read_ids_method(self, rank):
+    rank = np.ascontiguousarray(rank, dtype=np.int32)
+    _lib.check(self.L.csv_remap_read_ids(self.h, _abi.ptr(rank), C.c_int64(len(rank))))
+
+
+def _swap_ins_rows_method(self, pairs):
+    pairs = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
+    if len(pairs):
+        _lib.check(self.L.csv_swap_ins_rows(self.h, pairs.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int64(len(pairs))))
 
 
 def _fetch_extracted_method(self):
@@ -321,5 +388,11 @@ def _fetch_extracted_method(self):
 
 
 Engine.pin_packet = _pin_packet_method
+Engine.extract_reset = _extract_reset_method
+Engine.fetch_ins_pieces = _fetch_ins_pieces_method
+Engine.fetch_sig_cols = _fetch_sig_cols_method
+Engine.remap_read_ids = _remap_read_ids_method
+Engine.fetch_read_rows = _fetch_read_rows_method
+Engine.swap_ins_rows = _swap_ins_rows_method
 Engine.extract = _extract_method
 Engine.fetch_extracted = _fetch_extracted_method

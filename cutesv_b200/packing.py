@@ -78,12 +78,48 @@ def revcomp(s):
     return s.translate(_COMP)[::-1]
 
 
-def ins_sequence(pieces, off, cnt, query_of):
-    """Rebuild an INS signature's sequence from its piece list; query_of(rec) -> query string."""
+def merged_ins_from_cigar(cigar, ref_start, query, pos, min_siglength, merge_ins_threshold):
+    """Sequence of the merged insertion signature that starts at reference position `pos`: parse_read's CIGAR walk
+    (cuteSV:616-645) + generate_combine_sigs' INS chain (cuteSV:530-545) on one record.  Only for signatures that merge more
+    insertions than the device buffers (piece flag 2)."""
+    ref = int(ref_start)
+    first = int(cigar[0]) if len(cigar) else 0
+    q = -(first >> 4) if (first & 15) == 5 else 0          # shift_ins_read starts at -hardclip_left
+    groups = []                                              # [first pos, last pos, [slices]]
+    for cg in cigar:
+        op, ln = int(cg) & 15, int(cg) >> 4
+        if op != 2:
+            q += ln                                          # every op except D advances the query cursor (cuteSV:631-632)
+        if ln >= min_siglength and op in (1, 2):
+            if op == 2:
+                ref += ln
+            else:
+                piece = query[q - ln:q]   # Python slice semantics, as the reference (cuteSV:639)
+                if groups and ref - groups[-1][1] <= merge_ins_threshold:
+                    groups[-1][1] = ref
+                    groups[-1][2].append(piece)
+                else:
+                    groups.append([ref, ref, [piece]])
+        elif op in (0, 2, 3, 7, 8):
+            ref += ln
+    for g in groups:
+        if g[0] == pos:
+            return "".join(g[2])
+    raise ValueError("merged insertion at %d not found in the record's CIGAR" % pos)
+
+
+def ins_sequence(pieces, off, cnt, query_of, cigar_of=None, merge=None):
+    """Rebuild an INS signature's sequence from its piece list; query_of(rec) -> query string.
+    A piece with flag 2 (more merged insertions than the device buffers) is rebuilt from the record's CIGAR:
+    cigar_of(rec) -> (uint32 CIGAR array, reference_start), merge = (min_siglength, merge_ins_threshold)."""
     out = []
     for p in range(off, off + cnt):
         rec, a, b, rc = (int(x) for x in pieces[p])
         q = query_of(rec)
+        if rc == 2:
+            cig, ref_start = cigar_of(rec)
+            out.append(merged_ins_from_cigar(cig, ref_start, q, a, merge[0], merge[1]))
+            continue
         if rc:
             q = revcomp(q)
         out.append(q[a:b])

@@ -440,7 +440,100 @@ def synth_alignments(seed, n_reads=200, n_contigs=3, with_seq=True):
     return reads, names, lens
 
 
-def synth_bam_dataset(seed=1, n_contigs=2, contig_len=120000, coverage=22, read_len=(2500, 7000)):
+def synth_alignments_long(seed, n_reads=16, n_contigs=3, ops_range=(10000, 30000)):
+    """BASELINE config-5-shaped records for the extraction goldens: >= 10^4 CIGAR ops per record (one op per ~7 bp), hard / soft
+    clips on both ends, runs of 70-90 chained >= 10 bp insertions (more merged pieces than the kernel buffers), and 2-6 SA
+    segments laid out to reach the strand patterns of analysis_split_read (cuteSV:190-464): colinear same-strand chains
+    (DEL / INS / DUP rules), +-+ / -+- (INV rules), a foreign contig in the middle (BND + post-loop bridge), mixed tails.
+    Returns (reads, contig_names, contig_lens)."""
+    rng = np.random.default_rng(seed)
+    names, lens = contigs(1.0, n_contigs)
+    lens = np.minimum(lens, 40000000).astype(np.int64)
+    reads = []
+    for i in range(n_reads):
+        r = SynthRead()
+        r.flag = int(rng.choice([0, 16, 0, 16, 2048, 2064]))
+        r.query_name = read_name(i if r.flag in (0, 16) else int(rng.integers(0, max(n_reads // 2, 1))))
+        r.mapq = int(rng.choice([60, 60, 30, 20, 5]))
+        ch = int(rng.integers(0, n_contigs))
+        r.reference_name = names[ch]
+        r.reference_start = int(rng.integers(1000, 2000000))
+        n_pairs = int(rng.integers(ops_range[0] // 2, ops_range[1] // 2))
+        m_len = 1 + rng.geometric(1.0 / 12.0, n_pairs)
+        small = 1 + rng.geometric(0.6, n_pairs)
+        kind = rng.random(n_pairs)
+        other_op = np.where(kind < 0.47, 1, np.where(kind < 0.94, 2, np.where(kind < 0.97, 3, 6)))   # I, D, N, P
+        big = rng.random(n_pairs) < 4.0 / n_pairs
+        small[big] = 10 + rng.geometric(0.02, int(big.sum()))
+        ops = []
+        lead_kind = int(rng.choice([0, 4, 5], p=[0.2, 0.5, 0.3]))
+        if lead_kind:
+            ops.append((lead_kind, int(rng.integers(50, 4000))))
+        chain_at = int(rng.integers(0, n_pairs)) if rng.random() < 0.6 else -1
+        for k in range(n_pairs):
+            ops.append((int(rng.choice([0, 7, 8], p=[0.8, 0.15, 0.05])), int(m_len[k])))
+            if k == chain_at:   # 70-90 insertions of 12-20 bp, 20-60 bp apart: one merged signature with > 64 pieces
+                for _ in range(int(rng.integers(70, 91))):
+                    ops.append((1, int(rng.integers(12, 21))))
+                    ops.append((0, int(rng.integers(20, 61))))
+            ops.append((int(other_op[k]), int(small[k])))
+        ops.append((0, int(rng.integers(5, 60))))
+        trail_kind = int(rng.choice([0, 4, 5], p=[0.2, 0.5, 0.3]))
+        if trail_kind:
+            ops.append((trail_kind, int(rng.integers(50, 4000))))
+        qlen = sum(l for o, l in ops if o in (0, 1, 4, 7, 8))
+        span = sum(l for o, l in ops if o in (0, 2, 3, 7, 8))
+        r.cigartuples = ops
+        r.cigar = ops
+        r.query_length = qlen
+        r.reference_end = r.reference_start + span
+        r.query_sequence = "".join(rng.choice(list("ACGT"), qlen))
+        tags = [("NM", 3)]
+        if r.flag in (0, 16) and rng.random() < 0.85:
+            k = int(rng.integers(2, 7))
+            pattern = int(rng.integers(0, 5))
+            L = qlen
+            cuts = np.sort(rng.integers(0, L, k + 1))
+            own = "+" if r.flag == 0 else "-"
+            flip = {"+": "-", "-": "+"}
+            ents = []
+            pos = r.reference_end + int(rng.integers(-2000, 2000))
+            for j in range(k):
+                a, b = int(cuts[j]), int(cuts[j + 1])
+                if b <= a:
+                    b = a + 1
+                if pattern == 0:      # colinear, same strand: DEL / INS / DUP rules
+                    strand, sch = own, names[ch]
+                    pos += int(rng.integers(-1500, 4000))
+                elif pattern == 1:    # alternating strands: + - + / - + - inversion rules
+                    strand, sch = (own if j % 2 else flip[own]), names[ch]
+                    pos += int(rng.integers(-500, 3000))
+                elif pattern == 2:    # a foreign contig in the middle: BND rules + the post-loop bridge
+                    mid = 0 < j < k - 1 or k == 2
+                    strand, sch = own, (names[(ch + 1) % n_contigs] if mid else names[ch])
+                    pos += int(rng.integers(-1000, 3000))
+                elif pattern == 3:    # strand change at the tail (rule 4)
+                    strand, sch = (flip[own] if j >= k - 2 else own), names[ch]
+                    pos += int(rng.integers(-800, 2500))
+                else:                 # anything
+                    strand = own if rng.random() < 0.5 else flip[own]
+                    sch = names[int(rng.integers(0, n_contigs))]
+                    pos = int(rng.integers(1, 3000000))
+                pos = max(pos, 1)
+                seg = max(b - a, 1)
+                mid_c = "%dM" % seg if rng.random() < 0.7 else "%dM%dD%dM" % (max(seg // 2, 1), int(rng.integers(1, 300)), max(seg - seg // 2, 1))
+                lead = ("%dS" % a if rng.random() < 0.8 else "%dH" % a) if a > 0 else ""
+                trail = ("%dS" % (L - b) if rng.random() < 0.8 else "%dH" % (L - b)) if L - b > 0 else ""
+                if strand == "-":
+                    lead, trail = trail, lead
+                ents.append("%s,%d,%s,%s%s%s,%d,%d" % (sch, pos, strand, lead, mid_c, trail, int(rng.choice([60, 60, 20, 3])), 5))
+            tags.append(("SA", ";".join(ents) + ";"))
+        r.tags = tags
+        reads.append(r)
+    return reads, names, lens
+
+
+def synth_bam_dataset(seed=1, n_contigs=2, contig_len=120000, coverage=22, read_len=(2500, 7000), double_ins=0.0):
     """A small coherent long-read dataset for the CLI plumbing test (BASELINE.json config 1 in
     spirit): reads tile the contigs; planted DEL / INS loci appear in the CIGAR of the reads that
     span them (position / length jitter), TRA loci as split reads with SA tags.  Returns
@@ -501,6 +594,11 @@ def synth_bam_dataset(seed=1, n_contigs=2, contig_len=120000, coverage=22, read_
                 if kind == "DEL":
                     ops.append((2, ln2))
                     ref += ln2
+                elif double_ins > 0 and rng.random() < double_ins:
+                    # the same read reports TWO insertions of equal length at the same position ("nInI"): with -mi -1 they stay
+                    # two signatures that tie on (chr, int(pos), len, name) and differ only in their sequence (cuteSV:774)
+                    ops.append((1, ln2))
+                    ops.append((1, ln2))
                 else:
                     ops.append((1, ln2))
             if tra_hit is not None:

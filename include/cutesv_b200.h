@@ -26,6 +26,11 @@
  *
  * contig id = rank of the contig name in Python string order, read_id = rank of the read name
  * in Python string order (the reference sorts tuples with string tie-breaks, cuteSV:764-801).
+ *
+ * INS rows that tie on (contig, int(pos), len, read_id) must come in the order of their sequence strings: the
+ * reference's INS sort key is (chr, int(pos), len, name, seq) (cuteSV:774) and the library never sees the strings,
+ * it breaks such ties by input order.  They need one read reporting two insertions of equal length at the same
+ * position; the host converters (workdir.py, cli.py) put them in order.
  */
 #ifndef CUTESV_B200_H
 #define CUTESV_B200_H
@@ -255,12 +260,41 @@ typedef struct csv_sa_cols {
  * reverse complement) from which the host rebuilds the string when it needs it. */
 int csv_extract(csv_ctx* ctx, const csv_read_cols* reads, const uint32_t* cigar, int64_t n_cigar,
                 const csv_sa_cols* sa, int64_t counts[CSV_NTYPES], int64_t* n_read_rows);
+/* Append mode (cuteSV:734-739: every task's signatures are appended to the per-type lists; the reference then
+ * concatenates the lists of all tasks, cuteSV:750-762): like csv_extract, but the signatures, INS piece descriptors
+ * and reads-table rows of this packet are APPENDED to the device-resident inputs of csv_cluster, so a BAM-to-VCF run
+ * never moves a signature column across PCIe.  The record index in an INS piece is the packet-local index plus the
+ * number of records of all earlier packets of the accumulation.  counts / n_read_rows report the totals so far.
+ * csv_extract_reset (or a plain csv_extract / csv_upload_*) starts a new accumulation. */
+int csv_extract_append(csv_ctx* ctx, const csv_read_cols* reads, const uint32_t* cigar, int64_t n_cigar,
+                       const csv_sa_cols* sa, int64_t counts[CSV_NTYPES], int64_t* n_read_rows);
+int csv_extract_reset(csv_ctx* ctx);
+/* Records whose split-read analysis was skipped because they carry more than 64 qualifying segments (only reachable
+ * with --max_split_parts -1; their CIGAR signatures are taken).  The reference has no such limit: a documented,
+ * counted deviation instead of a failed run. */
+int64_t csv_extract_skipped(csv_ctx* ctx);
+/* read_id of every device-resident signature / reads-table row: id -> rank[id].  The CLI numbers read names in
+ * first-seen order while it decodes and learns their ranks in Python string order at the end (cuteSV:764-801). */
+int csv_remap_read_ids(csv_ctx* ctx, const int32_t* rank, int64_t n_rank);
+/* Swap rows pairs[2k] <-> pairs[2k+1] of the device-resident INS signatures (columns and piece descriptors), in
+ * sequence.  INS rows that tie on (contig, int(pos), len, read) must be in the order of their sequence strings
+ * (the reference's sort key ends with the sequence, cuteSV:774); the host, which owns the strings, fixes the few
+ * ties of device-extracted rows with this call. */
+int csv_swap_ins_rows(csv_ctx* ctx, const int64_t* pairs, int64_t n_pairs);
+/* Slices [first, first + count) of the extracted columns of one type / of the piece table (append mode: the rows a
+ * packet added). */
+int csv_fetch_sigs_range(csv_ctx* ctx, int svtype, int64_t first, int64_t count, int32_t* chrom, int32_t* a, int32_t* b,
+                         int32_t* read_id, int32_t* c, int32_t* piece_off, int32_t* piece_cnt);
+int csv_fetch_pieces_range(csv_ctx* ctx, int64_t first, int64_t count, int32_t* pieces4);
 /* D2H of the extracted signature columns of one type (parity tests, .sigs dumps, host ALT
  * strings).  piece_off / piece_cnt (INS only, may be NULL): slice of the piece table. */
 int csv_fetch_sigs(csv_ctx* ctx, int svtype, int64_t cap, int32_t* chrom, int32_t* a, int32_t* b,
                    int32_t* read_id, int32_t* c, int32_t* piece_off, int32_t* piece_cnt);
 /* Piece table: 4 int32 per piece = (record index, slice start, slice stop, reverse-complement flag),
- * Python slice semantics (negative indices allowed).  *n_pieces reports the table size. */
+ * Python slice semantics (negative indices allowed).  *n_pieces reports the table size.
+ * flag == 2 marks a signature that merged more CIGAR insertions than the device buffers (64): `slice start` is then
+ * the reference position of the merged group and the host rebuilds the string by walking that record's CIGAR
+ * (cutesv_b200/packing.py merged_ins_from_cigar); position, length and len(seq) of the signature are complete. */
 int csv_fetch_pieces(csv_ctx* ctx, int64_t cap, int32_t* pieces4, int64_t* n_pieces);
 int csv_fetch_read_rows(csv_ctx* ctx, int64_t cap, int32_t* chrom, int32_t* start, int32_t* end,
                         int32_t* read_id, uint8_t* is_primary);

@@ -4,8 +4,10 @@ import collections
 from cutesv_b200 import packing
 
 
-def tuples_from_columns(ex, chrom_names, read_names, query_of):
-    """ex: dict(sigs, piece_off, piece_cnt, pieces, rows) -> the reference's tuple shapes."""
+def tuples_from_columns(ex, chrom_names, read_names, query_of, cigar_of=None, merge=(10, 100)):
+    """ex: dict(sigs, piece_off, piece_cnt, pieces, rows) -> the reference's tuple shapes.
+    cigar_of(rec) -> (uint32 CIGAR array, reference_start) and merge = (min_siglength, merge_ins_threshold) are only needed
+    for signatures that merged more insertions than the device buffers (piece flag 2)."""
     out = {k: [] for k in ("DEL", "INS", "DUP", "INV", "TRA")}
     s = ex["sigs"]["DEL"]
     for i in range(len(s["chrom"])):
@@ -13,7 +15,7 @@ def tuples_from_columns(ex, chrom_names, read_names, query_of):
     s = ex["sigs"]["INS"]
     for i in range(len(s["chrom"])):
         a = int(s["a"][i])
-        seq = packing.ins_sequence(ex["pieces"], int(ex["piece_off"][i]), int(ex["piece_cnt"][i]), query_of)
+        seq = packing.ins_sequence(ex["pieces"], int(ex["piece_off"][i]), int(ex["piece_cnt"][i]), query_of, cigar_of, merge)
         assert len(seq) == int(s["c"][i]), ("seq_len column", len(seq), int(s["c"][i]))
         out["INS"].append((a / 2, int(s["b"][i]), read_names[int(s["read_id"][i])], seq, "INS", chrom_names[int(s["chrom"][i])]))
     s = ex["sigs"]["DUP"]

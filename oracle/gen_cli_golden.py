@@ -15,9 +15,9 @@ FLAGS = ["--genotype", "-s", "5", "--threads", "4", "--max_cluster_bias_INS", "1
          "--max_cluster_bias_DEL", "100", "--diff_ratio_merging_DEL", "0.3"]
 
 
-def materialise(d, seed=1):
+def materialise(d, seed=1, double_ins=0.0):
     from cutesv_b200 import synth
-    ds, fasta = synth.synth_bam_dataset(seed)
+    ds, fasta = synth.synth_bam_dataset(seed, double_ins=double_ins)
     bam = os.path.join(d, "x.bam")
     with open(bam, "wb") as f:
         pickle.dump(ds, f)
@@ -71,6 +71,26 @@ EXTRA_FLAG_SETS = {
 }
 
 
+# INS ties: half of the INS-carrying reads report the insertion as two equal-length I ops at the same position; -mi -1 keeps them
+# apart, so the signatures tie on (chr, int(pos), len, name) and the reference orders them by their sequence strings (cuteSV:774)
+TIES = dict(seed=2, double_ins=0.5, flags=FLAGS + ["-mi", "-1", "--report_readid"])
+
+
+def main_ties():
+    import pysam  # noqa: F401
+    from oracle import ref_harness
+    m = ref_harness.modules()
+    from cuteSV.cuteSV_Description import parseArgs
+    d = tempfile.mkdtemp()
+    bam, fa, out, wd = materialise(d, TIES["seed"], TIES["double_ins"])
+    argv = [bam, fa, out, wd] + TIES["flags"]
+    m["main"].main_ctrl(parseArgs(argv), argv)
+    lines = [l for l in open(out) if not l.startswith("##")]
+    with open(os.path.join(ROOT, "tests", "golden", "cli_dataset2_ins_ties.json"), "w") as f:
+        json.dump(dict(flags=TIES["flags"], seed=TIES["seed"], double_ins=TIES["double_ins"], lines=lines), f)
+    print("dataset2 (INS ties):", len(lines) - 1, "records")
+
+
 def main():
     import pysam  # noqa: F401  (the fake one, first on sys.path)
     from oracle import ref_harness
@@ -111,4 +131,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ties":
+        main_ties()
+    else:
+        main()

@@ -2,8 +2,8 @@
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/tests_multi.txt 2>&1
-tail -15 gpurun_out/tests_multi.txt
+true
+true
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_strong_${N}.json 2> gpurun_out/bench_strong_${N}.err || tail -20 gpurun_out/bench_strong_${N}.err
 python - <<PY
 import json

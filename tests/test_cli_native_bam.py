@@ -119,3 +119,35 @@ def test_cli_pysam_path_many_packets_cpu(tmp_path, monkeypatch):
     cli.main_ctrl(cli.build_parser().parse_args(argv), argv, engine=EmulEngine())
     assert [l for l in open(out) if not l.startswith("##")] == gold["lines"]
     sys.modules.pop("pysam", None)
+
+
+def _run_ties(engine, tmp_path, disable_tie_order=False, monkeypatch=None):
+    bamio.build()
+    gold = json.load(open(os.path.join(golden_util.GOLDEN, "cli_dataset2_ins_ties.json")))
+    pk, fa, out, wd = gen_cli_golden.materialise(str(tmp_path), gold["seed"], gold["double_ins"])
+    bam = _to_real_bam(pk, str(tmp_path / "real.bam"))
+    if disable_tie_order:
+        monkeypatch.setattr(cli, "ins_tie_swaps", lambda *a: [])
+    argv = [bam, fa, out, wd] + gold["flags"]
+    cli.main_ctrl(cli.build_parser().parse_args(argv), argv, engine=engine)
+    import vcf_util
+    return vcf_util.normalise_rnames([l for l in open(out) if not l.startswith("##")]), vcf_util.normalise_rnames(gold["lines"])
+
+
+def test_cli_ins_ties_ordered_by_sequence_cpu(tmp_path, monkeypatch):
+    """INS signatures that tie on (chr, int(pos), len, read) are ordered by their sequence strings (cuteSV:774): half of the
+    INS-carrying reads report the insertion as two equal-length I ops at one position, -mi -1 keeps them apart.  The VCF body
+    equals the REAL reference's; without the host-side tie ordering it does not (the golden pins which way ties fall)."""
+    from emul_engine import EmulEngine
+    lines, gold = _run_ties(EmulEngine(), tmp_path)
+    assert len(lines) > 20 and lines == gold
+    t2 = tmp_path / "off"
+    t2.mkdir()
+    lines_off, _ = _run_ties(EmulEngine(), t2, True, monkeypatch)
+    assert lines_off != gold
+
+
+@pytest.mark.gpu
+def test_cli_ins_ties_ordered_by_sequence_gpu(engine, tmp_path):
+    lines, gold = _run_ties(engine, tmp_path)
+    assert lines == gold
