@@ -415,25 +415,10 @@ class _NameIds(object):
 
 def _write_workdir(tmp, sigs, reads_cols, chrom_names, read_names, ins_seq, write_old_sigs):
     """--retain_work_dir: the reference's <TYPE>.pickle / sigindex.pickle layout (cuteSV:817-857)."""
-    tuples = {}
-    s = sigs["DEL"]
-    tuples["DEL"] = [(int(s["a"][i]), int(s["b"][i]), read_names[int(s["read_id"][i])], "DEL", chrom_names[int(s["chrom"][i])])
-                     for i in range(len(s["chrom"]))]
-    s = sigs["INS"]
-    tuples["INS"] = [((int(s["a"][i]) // 2 if int(s["a"][i]) % 2 == 0 else int(s["a"][i]) / 2), int(s["b"][i]), read_names[int(s["read_id"][i])],
-                      ins_seq[i], "INS", chrom_names[int(s["chrom"][i])]) for i in range(len(s["chrom"]))]
-    s = sigs["DUP"]
-    tuples["DUP"] = [(int(s["a"][i]), int(s["b"][i]), read_names[int(s["read_id"][i])], "DUP", chrom_names[int(s["chrom"][i])])
-                     for i in range(len(s["chrom"]))]
-    s = sigs["INV"]
-    tuples["INV"] = [("++" if int(s["c"][i]) == 0 else "--", int(s["a"][i]), int(s["b"][i]), read_names[int(s["read_id"][i])], "INV",
-                      chrom_names[int(s["chrom"][i])]) for i in range(len(s["chrom"]))]
-    s = sigs["TRA"]
-    tuples["TRA"] = [("ABCD"[int(s["c"][i]) & 3], int(s["a"][i]), chrom_names[int(s["c"][i]) >> 2], int(s["b"][i]),
-                      read_names[int(s["read_id"][i])], "TRA", chrom_names[int(s["chrom"][i])]) for i in range(len(s["chrom"]))]
+    tuples = {t: workdir.columns_to_tuples(t, sigs[t], chrom_names, read_names, ins_seq) for t in workdir.TYPES}
     r = reads_cols
-    tuples["reads"] = [(int(r["start"][i]), int(r["end"][i]), int(r["is_primary"][i]), read_names[int(r["read_id"][i])],
-                        chrom_names[int(r["chrom"][i])]) for i in range(len(r["chrom"]))]
+    tuples["reads"] = list(zip(r["start"].tolist(), r["end"].tolist(), r["is_primary"].tolist(), [read_names[i] for i in r["read_id"].tolist()],
+                               [chrom_names[i] for i in r["chrom"].tolist()]))
     workdir.write_workdir(tmp, tuples)
     if write_old_sigs:  # legacy text dumps, cuteSV:766-816
         fmt = {"DEL": lambda e: "%s\t%s\t%d\t%d\t%s\n" % (e[-2], e[-1], e[0], e[1], e[2]),

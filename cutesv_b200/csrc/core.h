@@ -89,6 +89,11 @@ struct Emit {
     Counters* ctr;
     const double* pow_half; // pow_half[n] = n ** 0.5 as libm pow evaluates it (cal_CIPOS)
     Limits lim;
+    // Append cursor, (candidates << 32) | names, in a cache line of its own: ONE returning atomic per emitted row.  (Two
+    // atomics per row on ctr->n_cand / n_names + an atomicMax on ctr->max_support, all in the Counters line, serialise at
+    // one L2 slice at ~1 ns each: ~60 us per 19 k rows -- that, not the arithmetic, was the floor of the cluster kernels.)
+    // null: the counters themselves are the cursor (single-threaded emulator).
+    unsigned long long* cursor;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -528,8 +533,20 @@ struct IndelArena {
 // two halves so that a caller can issue the two returning atomics early and look at their results
 // only after other work (their round trip to L2 is ~1 us)
 CSV_HD void emit_reserve_issue(const Emit& E, uint32_t n_names, uint32_t* slot, uint32_t* noff) {
+#if defined(__CUDA_ARCH__)
+    if (E.cursor) {
+        const unsigned long long old = atomicAdd(E.cursor, (1ull << 32) | (unsigned long long)n_names);
+        *slot = (uint32_t)(old >> 32);
+        *noff = (uint32_t)old;
+        return;
+    }
+#endif
     *slot = atomic_add_u32(&E.ctr->n_cand, 1u);
     *noff = atomic_add_u32(&E.ctr->n_names, n_names);
+}
+// largest allele support seen (sizes the n ** 0.5 table): a plain look first, the atomic only when it would change something
+CSV_HD void note_support(const Emit& E, uint32_t n) {
+    if (n > *(volatile uint32_t*)&E.ctr->max_support) atomic_max_u32(&E.ctr->max_support, n);
 }
 CSV_HD bool emit_reserve_check(const Emit& E, uint32_t n_names, uint32_t s, uint32_t o) {
     if (s >= E.lim.cap_cand) { atomic_or_u32(&E.ctr->status, ST_CAND_OVERFLOW); return false; }
@@ -547,9 +564,12 @@ CSV_HD bool emit_reserve(const Emit& E, uint32_t n_names, uint32_t* slot, uint32
 // on the m signatures sidx[s..s+m) of one chain cluster.  M = pow2 >= m arena capacity.
 // kslot = global kept-cluster slot (indexes Emit::cnt); returns nothing, emits rows.
 // ------------------------------------------------------------------------------------------
-template <class Team>
+// SV / KEEPALL >= 0 fix the SV type / "remain_reads_ratio keeps every member" at compile time (the hot warp kernels are
+// instantiated per type so that the other type's branches and the trimming sorts are not part of their instruction stream).
+template <class Team, int SV = -1, int KEEPALL = -1>
 CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M, char* arena, int64_t* red,
-                          const ClusterParams& P, int svtype, uint32_t kslot, const Emit& E) {
+                          const ClusterParams& P, int svtype_rt, uint32_t kslot, const Emit& E) {
+    const int svtype = SV >= 0 ? SV : svtype_rt;
     const int t = tm.tid();
     IndelArena A(arena, M);
     int32_t* ar_a = A.A1;
@@ -677,6 +697,7 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
         if (n < P.min_support_allele) continue;
         int64_t remain = (int64_t)(P.keep * (double)n);
         if (remain < 1) remain = 1;
+        if (KEEPALL == 1) remain = n;   // (the host only picks this instantiation when keep == 1.0)
         int64_t pp = 0, pl = 0;
         for (int i = t; i < n; i += Team::SIZE) { uint32_t e = V3[st + i]; pp += D_pos[e]; pl += D_len[e]; }
         const int64_t sp = team_sum(tm, pp, red);
@@ -719,7 +740,7 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
             if (t == 0) emit_reserve_issue(E, (uint32_t)n, &slot, &noff);   // results are looked at after the std work
             reserved = true;
         }
-        if (remain < n) {
+        if (KEEPALL != 1 && remain < n) {
             // keep only the `remain` closest members (remain_reads_ratio < 1)
             K128* R = A.A0;
             const int MR = pow2ceil(n);
@@ -786,7 +807,7 @@ CSV_HD void indel_cluster(Team tm, const IndelView& in, int64_t s, int m, int M,
         int64_t ok = 0;
         if (t == 0) {
             if ((uint32_t)n >= E.lim.pow_n) atomic_or_u32(&E.ctr->status, ST_POW_TABLE);
-            atomic_max_u32(&E.ctr->max_support, (uint32_t)n);
+            note_support(E, (uint32_t)n);
             if (!reserved) emit_reserve_issue(E, (uint32_t)n, &slot, &noff);
             ok = emit_reserve_check(E, (uint32_t)n, slot, noff) ? 1 : 0;
             red[0] = ok; red[1] = slot; red[2] = noff;

@@ -113,7 +113,7 @@ struct LaneWork {
     cudaEvent_t ev_join = nullptr;
     bool used = false;
     DBuf keys_a, keys_b, vals_a, vals_b, hist, lb_status, bkt, bkt_flags, big_list, giant_list, giant_arena;
-    DBuf boff, rec_a, rec_b, recc_a, recc_b, big_bkt;   // filter-first INS/DEL front end
+    DBuf boff, rec_a, rec_b, recc_a, recc_b, big_bkt, rest_list;   // filter-first INS/DEL front end, k_cluster_small's rest list
     SmallWork small;
 };
 static constexpr int N_LANES = CSV_NTYPES;
@@ -149,13 +149,15 @@ struct csv_ctx {
     // sort workspace
     DBuf keys_a, keys_b, vals_a, vals_b, hist, lb_status, tickets, bkt, bkt_flags;
     DBuf boff, rec_a, rec_b, recc_a, recc_b, big_bkt;   // filter-first INS/DEL front end (per lane, see LaneWork)
-    DBuf scan_carry;
+    DBuf rest_list;                  // kept clusters k_cluster_small left to the general kernel (per lane)
+    DBuf scan_carry, emit_cursor;
     DBuf d_epoch;                    // look-back generation base, bumped by the first kernel of every csv_cluster
     uint32_t epoch_host = 0;
     bool small_chain[CSV_NTYPES] = {false, false, false, false, false};   // chained-sorts fallback after ST_BIG_RUN
     bool prefilter_enabled = true;
     bool bucket_sort_enabled = true;
     bool records_enabled = true;
+    bool small_path_enabled = true;
     int64_t pair_cap_override = 0;
     int ticket_next = 0;
     SmallWork small;
@@ -232,12 +234,15 @@ static void kprof_end(csv_ctx* c);
     } while (0)
 #define LAUNCH(ctx, kernel, grid, block, smem, ...) LAUNCH_NAMED(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
 
-template <int KIND>
+// KIND: the per-type routine of the warp kernel (0 INS/DEL generic, 1 DUP, 2 INV, 3 TRA, 4-7 INS/DEL specialisations, see
+// run_cluster); the CTA kernel (rare big clusters) always uses the generic routine BKIND in 0..3
+template <int KIND, int BKIND>
 static void launch_cluster_kind(csv_ctx* c, const TypeJob& J, const Emit& E, Counters* ctr, uint32_t* work, size_t smem_warp) {
-    static const char* const nm_w[4] = {"k_cluster_warp<INDEL>", "k_cluster_warp<DUP>", "k_cluster_warp<INV>", "k_cluster_warp<TRA>"};
+    static const char* const nm_w[8] = {"k_cluster_warp<INDEL>", "k_cluster_warp<DUP>", "k_cluster_warp<INV>", "k_cluster_warp<TRA>",
+                                        "k_cluster_warp<DEL>", "k_cluster_warp<INS>", "k_cluster_warp<DEL,keep-all>", "k_cluster_warp<INS,keep-all>"};
     static const char* const nm_b[4] = {"k_cluster_block<INDEL>", "k_cluster_block<DUP>", "k_cluster_block<INV>", "k_cluster_block<TRA>"};
     LAUNCH_NAMED(c, nm_w[KIND], (k_cluster_warp<KIND>), c->n_sm * 3, CL_THREADS, smem_warp, J, E, ctr, work);
-    LAUNCH_NAMED(c, nm_b[KIND], (k_cluster_block<KIND>), c->n_sm, CL_THREADS, (size_t)BLOCK_M * ARENA_PER_MAX, J, E, ctr);
+    LAUNCH_NAMED(c, nm_b[BKIND], (k_cluster_block<BKIND>), c->n_sm, CL_THREADS, (size_t)BLOCK_M * ARENA_PER_MAX, J, E, ctr);
 }
 
 static int grid_for(const csv_ctx* c, int64_t n, int block, int per_sm = 8) {
@@ -384,6 +389,7 @@ extern "C" int csv_create(int device, void* stream, csv_ctx** out) {
     if (const char* e = getenv("CUTESV_B200_GRAPHS")) c->graphs_enabled = atoi(e) != 0;
     if (const char* e = getenv("CUTESV_B200_BUCKET_SORT")) c->bucket_sort_enabled = atoi(e) != 0;
     if (const char* e = getenv("CUTESV_B200_RECORDS")) c->records_enabled = atoi(e) != 0;
+    if (const char* e = getenv("CUTESV_B200_SMALL_PATH")) c->small_path_enabled = atoi(e) != 0;
     if (const char* e = getenv("CUTESV_B200_SMALL_CHAIN")) for (int t = 0; t < CSV_NTYPES; t++) c->small_chain[t] = atoi(e) != 0;
     for (int s = 0; s < CSV_ST_COUNT; s++) c->stage_ms[s] = 0.f;
     cudaError_t e3 = cudaMallocHost((void**)&c->h_counters, sizeof(Counters));
@@ -391,12 +397,17 @@ extern "C" int csv_create(int device, void* stream, csv_ctx** out) {
     int rc = upload_tables(c, 1u << 16);
     if (rc != CSV_OK) { delete c; return rc; }
     CU(c->d_epoch.ensure(64, true));
+    CU(c->emit_cursor.ensure(256, true));
     // opt in to large dynamic shared memory for the cluster kernels
     const int smem_warp = (CL_THREADS / 32) * WARP_M * ARENA_PER_MAX + (CL_THREADS / 32) * 40 * 8;
     CU(cudaFuncSetAttribute(k_cluster_warp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
     CU(cudaFuncSetAttribute(k_cluster_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
     CU(cudaFuncSetAttribute(k_cluster_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
     CU(cudaFuncSetAttribute(k_cluster_warp<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
+    CU(cudaFuncSetAttribute(k_cluster_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
+    CU(cudaFuncSetAttribute(k_cluster_warp<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
+    CU(cudaFuncSetAttribute(k_cluster_warp<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
+    CU(cudaFuncSetAttribute(k_cluster_warp<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_warp));
     CU(cudaFuncSetAttribute(k_cluster_block<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
     CU(cudaFuncSetAttribute(k_cluster_block<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
     CU(cudaFuncSetAttribute(k_cluster_block<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_M * ARENA_PER_MAX));
@@ -416,7 +427,7 @@ extern "C" int csv_destroy(csv_ctx* c) {
                    &c->small.perm_a, &c->small.perm_b, &c->small.sel, &c->small.u_chrom, &c->small.u_a, &c->small.u_b,
                    &c->small.u_rid, &c->small.u_c, &c->boff, &c->rec_a, &c->rec_b, &c->recc_a, &c->recc_b, &c->big_bkt, &c->d_epoch,
                    &c->d_len_eff, &c->g_send, &c->g_recv, &c->g_cand, &c->g_geno, &c->g_names, &c->g_scratch, &c->cal_in0, &c->cal_in1,
-                   &c->cal_out, &c->aln_flag, &c->scan_carry, &c->win_rec};
+                   &c->cal_out, &c->aln_flag, &c->scan_carry, &c->win_rec, &c->rest_list, &c->emit_cursor};
     for (DBuf* b : all) b->release();
     for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->comm) comm_destroy(c);
@@ -426,7 +437,7 @@ extern "C" int csv_destroy(csv_ctx* c) {
         if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
         if (L.ev_join) cudaEventDestroy(L.ev_join);
         DBuf* lb[] = {&L.keys_a, &L.keys_b, &L.vals_a, &L.vals_b, &L.hist, &L.lb_status, &L.bkt, &L.bkt_flags, &L.big_list, &L.giant_list, &L.giant_arena,
-                      &L.boff, &L.rec_a, &L.rec_b, &L.recc_a, &L.recc_b, &L.big_bkt,
+                      &L.boff, &L.rec_a, &L.rec_b, &L.recc_a, &L.recc_b, &L.big_bkt, &L.rest_list,
                       &L.small.k_rid, &L.small.k_b, &L.small.k_prim, &L.small.perm_a, &L.small.perm_b, &L.small.sel, &L.small.u_chrom, &L.small.u_a,
                       &L.small.u_b, &L.small.u_rid, &L.small.u_c};
         for (DBuf* b : lb) b->release();
@@ -745,6 +756,7 @@ static Emit make_emit(csv_ctx* c) {
     E.lim.cap_cand = c->cap_cand;
     E.lim.cap_names = c->cap_names;
     E.lim.pow_n = c->pow_n;
+    E.cursor = c->emit_cursor.as<unsigned long long>();
     return E;
 }
 
@@ -784,11 +796,31 @@ static int run_segment_and_cluster(csv_ctx* c, TypeJob& J, int t, uint32_t kslot
     const size_t smem_warp = (size_t)(CL_THREADS / 32) * WARP_M * ARENA_PER_MAX + (CL_THREADS / 32) * 40 * 8;
     if (c->ticket_next >= (int)LB_ORDINALS) return set_err(CSV_E_STATE, "ticket pool exhausted");
     uint32_t* work = c->tickets.as<uint32_t>() + c->ticket_next++;  // zeroed per call
+    const bool keep_all = J.cp.keep >= 1.0;
+    J.rest_list = nullptr; J.n_rest = nullptr;
+    if (kind_of(t) == 0 && keep_all && J.small_path) {
+        // clusters of <= 32 members: register kernel; it lists the others for the general kernel
+        CU(c->rest_list.ensure((size_t)c->kept_cap[t] * 4 + 64));
+        if (c->ticket_next + 2 >= (int)LB_ORDINALS) return set_err(CSV_E_STATE, "ticket pool exhausted");
+        uint32_t* work_s = c->tickets.as<uint32_t>() + c->ticket_next++;
+        uint32_t* n_rest = c->tickets.as<uint32_t>() + c->ticket_next++;
+        TypeJob JS = J;
+        JS.rest_list = c->rest_list.as<uint32_t>();
+        // (the small kernel counts the listed clusters in ctr->pad[1] of... a ticket word: see below)
+        JS.n_rest = n_rest;
+        if (t == CSV_INS) LAUNCH_NAMED(c, "k_cluster_small<INS>", (k_cluster_small<true>), c->n_sm * 6, 256, 0, JS, E, ctr, work_s, n_rest);
+        else LAUNCH_NAMED(c, "k_cluster_small<DEL>", (k_cluster_small<false>), c->n_sm * 6, 256, 0, JS, E, ctr, work_s, n_rest);
+        J.rest_list = c->rest_list.as<uint32_t>();
+        J.n_rest = n_rest;
+    }
     switch (kind_of(t)) {   // one per-type routine per kernel instantiation (instruction-cache footprint)
-        case 0: launch_cluster_kind<0>(c, J, E, ctr, work, smem_warp); break;
-        case 1: launch_cluster_kind<1>(c, J, E, ctr, work, smem_warp); break;
-        case 2: launch_cluster_kind<2>(c, J, E, ctr, work, smem_warp); break;
-        default: launch_cluster_kind<3>(c, J, E, ctr, work, smem_warp); break;
+        case 0:
+            if (t == CSV_DEL) { if (keep_all) launch_cluster_kind<6, 0>(c, J, E, ctr, work, smem_warp); else launch_cluster_kind<4, 0>(c, J, E, ctr, work, smem_warp); }
+            else { if (keep_all) launch_cluster_kind<7, 0>(c, J, E, ctr, work, smem_warp); else launch_cluster_kind<5, 0>(c, J, E, ctr, work, smem_warp); }
+            break;
+        case 1: launch_cluster_kind<1, 1>(c, J, E, ctr, work, smem_warp); break;
+        case 2: launch_cluster_kind<2, 2>(c, J, E, ctr, work, smem_warp); break;
+        default: launch_cluster_kind<3, 3>(c, J, E, ctr, work, smem_warp); break;
     }
     stage_end(c, CSV_ST_CLUSTER);
     return CSV_OK;
@@ -908,6 +940,7 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
         J.iv.recc = with_c ? c->recc_a.as<int32_t>() : nullptr;
     }
     J.iv.is_ins = t == CSV_INS ? 1 : 0;
+    J.small_path = c->small_path_enabled ? 1 : 0;
     return run_segment_and_cluster(c, J, t, kslot_base);
 }
 
@@ -992,7 +1025,7 @@ static void lane_swap(csv_ctx* c, LaneWork& L) {
     std::swap(c->hist, L.hist); std::swap(c->lb_status, L.lb_status); std::swap(c->bkt, L.bkt); std::swap(c->bkt_flags, L.bkt_flags);
     std::swap(c->big_list, L.big_list); std::swap(c->giant_list, L.giant_list); std::swap(c->giant_arena, L.giant_arena);
     std::swap(c->boff, L.boff); std::swap(c->rec_a, L.rec_a); std::swap(c->rec_b, L.rec_b); std::swap(c->recc_a, L.recc_a);
-    std::swap(c->recc_b, L.recc_b); std::swap(c->big_bkt, L.big_bkt);
+    std::swap(c->recc_b, L.recc_b); std::swap(c->big_bkt, L.big_bkt); std::swap(c->rest_list, L.rest_list);
     std::swap(c->small, L.small);
 }
 static int ensure_small(csv_ctx* c, size_t ns) {
@@ -1084,7 +1117,7 @@ static int enqueue_cluster(csv_ctx* c, uint32_t type_mask) {
     // fresh look-back generation, zeroed tickets and counters.  (The per-cluster row counts `cnt` need no clearing: every
     // kept-cluster slot below n_kept[t] is written by a cluster kernel and the order scans stop at n_kept[t].)
     LAUNCH(c, k_begin, 1, 256, 0, c->d_epoch.as<uint32_t>(), c->tickets.as<uint32_t>(), (int)LB_ORDINALS, c->counters.as<uint32_t>(),
-           (int)(sizeof(Counters) / 4));
+           (int)(sizeof(Counters) / 4), c->emit_cursor.as<unsigned long long>());
     Counters* ctr = c->counters.as<Counters>();
     uint32_t kslot_base = 0;
     // fork: every lane's chain starts after the resets above; join before `order`
@@ -1166,7 +1199,7 @@ static int enqueue_cluster(csv_ctx* c, uint32_t type_mask) {
         }
         // final order; the same pass counts the genotype windows per bin
         LAUNCH(c, k_permute, grid_for(c, c->cap_cand, 256, 4), 256, 0, c->cand_tmp.as<csv_cand>(), c->cnt.as<uint32_t>(), ctr, c->cap_cand,
-               c->cand.as<csv_cand>(), G);
+               c->cand.as<csv_cand>(), G, c->emit_cursor.as<unsigned long long>());
     }
     stage_end(c, CSV_ST_ORDER);
     // ---- genotype ----

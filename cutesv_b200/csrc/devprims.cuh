@@ -121,8 +121,9 @@ struct TileSync {
 static constexpr uint32_t LB_ORDINALS = 1024;
 // first node of every csv_cluster call: fresh look-back generation, zeroed ticket words and counters (one launch
 // instead of a kernel and two memsets)
-__global__ void __launch_bounds__(256) k_begin(uint32_t* epoch, uint32_t* tickets, int n_tickets, uint32_t* counters, int n_counters) {
-    if (threadIdx.x == 0) *epoch += 1u;
+__global__ void __launch_bounds__(256) k_begin(uint32_t* epoch, uint32_t* tickets, int n_tickets, uint32_t* counters, int n_counters,
+                                               unsigned long long* cursor) {
+    if (threadIdx.x == 0) { *epoch += 1u; *cursor = 0ull; }
     for (int i = threadIdx.x; i < n_tickets; i += 256) tickets[i] = 0u;
     for (int i = threadIdx.x; i < n_counters; i += 256) counters[i] = 0u;
 }

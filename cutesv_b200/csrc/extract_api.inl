@@ -57,6 +57,7 @@ static int extract_impl(csv_ctx* c, const csv_read_cols* reads, const uint32_t* 
     for (int k = 0; k < 7; k++) { rc = ex_upload(c, X.r[k], rsrc[k], (size_t)n * 4); if (rc) return rc; }
     rc = ex_upload(c, X.cigar_off, reads->cigar_off, (size_t)(n + 1) * 8); if (rc) return rc;
     rc = ex_upload(c, X.sa_off, reads->sa_off, (size_t)(n + 1) * 8); if (rc) return rc;
+    CU(X.cigar.ensure((size_t)n_cigar * 4 + 2 * EX_SLOT_BYTES));   // the bulk copies of k_extract read whole tiles
     rc = ex_upload(c, X.cigar, cigar, (size_t)n_cigar * 4); if (rc) return rc;
     const void* ssrc[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (n_sa) { ssrc[0] = sa->chrom; ssrc[1] = sa->pos0; ssrc[2] = sa->strand; ssrc[3] = sa->mapq; ssrc[4] = sa->first_clip; ssrc[5] = sa->last_clip; ssrc[6] = sa->ref_span; }
@@ -112,7 +113,13 @@ static int extract_impl(csv_ctx* c, const csv_read_cols* reads, const uint32_t* 
         P.min_read_len = c->P.min_read_len; P.min_siglength = c->P.min_siglength; P.merge_del_threshold = c->P.merge_del_threshold;
         P.merge_ins_threshold = c->P.merge_ins_threshold;
         stage_begin(c, CSV_ST_EXTRACT);
-        if (n > 0) LAUNCH(c, k_extract, grid_for(c, n * 32, EX_THREADS, 8), EX_THREADS, 0, R, X.cigar.as<uint32_t>(), S, P, O, (int32_t)X.n_records);
+        if (n > 0) {
+            int per_sm = 1;
+            CU(cudaFuncSetAttribute(k_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM_BYTES));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extract, EX_THREADS, EX_SMEM_BYTES));
+            LAUNCH(c, k_extract, grid_for(c, n * 32, EX_THREADS, std::max(per_sm, 1)), EX_THREADS, EX_SMEM_BYTES, R, X.cigar.as<uint32_t>(), S, P, O,
+                   (int32_t)X.n_records, dc + 9);
+        }
         stage_end(c, CSV_ST_EXTRACT);
         CU(cudaMemcpyAsync(X.h_counters, dc, 16 * 4, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));

@@ -37,6 +37,9 @@ struct TypeJob {
     uint32_t* giant_list;
     uint32_t big_cap, giant_cap;
     char* giant_arena;
+    int small_path;          // INS / DEL: clusters of <= 32 members go through the register kernel (k_cluster_small) first
+    uint32_t* rest_list;     // ... which lists the others here (kept-cluster ordinals); null: the general kernel takes every cluster
+    const uint32_t* n_rest;
 };
 
 __device__ __forceinline__ int64_t job_n(const TypeJob& J) { return J.n_dev ? (int64_t)*J.n_dev : J.n_host; }
@@ -730,10 +733,15 @@ __global__ void k_other_gather(const int32_t* __restrict__ chrom, const int32_t*
 // KIND selects the one per-type routine a kernel instantiation contains (0 INS/DEL, 1 DUP, 2 INV, 3 TRA):
 // one routine per kernel keeps the hot code inside the instruction cache.
 __host__ __device__ constexpr int kind_of(int svtype) { return (svtype == CSV_DEL || svtype == CSV_INS) ? 0 : svtype == CSV_DUP ? 1 : svtype == CSV_INV ? 2 : 3; }
+// KIND 4..7: INS / DEL with the type (and "every member is kept") fixed at compile time: DEL, INS, DEL keep-all, INS keep-all
 template <int KIND, class Team>
 __device__ __forceinline__ void run_cluster(Team tm, const TypeJob& J, int64_t s, int m, int M, char* arena, int64_t* red,
                                             uint32_t kslot, const Emit& E) {
-    if (KIND == 0) indel_cluster(tm, J.iv, s, m, M, arena, red, J.cp, J.svtype, kslot, E);
+    if (KIND == 4) indel_cluster<Team, CSV_DEL, 0>(tm, J.iv, s, m, M, arena, red, J.cp, J.svtype, kslot, E);
+    else if (KIND == 5) indel_cluster<Team, CSV_INS, 0>(tm, J.iv, s, m, M, arena, red, J.cp, J.svtype, kslot, E);
+    else if (KIND == 6) indel_cluster<Team, CSV_DEL, 1>(tm, J.iv, s, m, M, arena, red, J.cp, J.svtype, kslot, E);
+    else if (KIND == 7) indel_cluster<Team, CSV_INS, 1>(tm, J.iv, s, m, M, arena, red, J.cp, J.svtype, kslot, E);
+    else if (KIND == 0) indel_cluster(tm, J.iv, s, m, M, arena, red, J.cp, J.svtype, kslot, E);
     else if (KIND == 1) dup_cluster(tm, J.sv, s, m, M, arena, red, J.cp, kslot, E);
     else if (KIND == 2) inv_cluster(tm, J.sv, s, m, M, arena, red, J.cp, kslot, E);
     else tra_cluster(tm, J.sv, s, m, M, arena, red, J.cp, kslot, E);
@@ -757,6 +765,221 @@ __device__ __forceinline__ int cluster_size_warp(const TypeJob& J, int64_t s, in
     return m;  // > limit
 }
 
+// ------------------------------------------------------------------------------------------
+// INS / DEL clusters of at most 32 members, every member kept (remain_reads_ratio >= 1): the whole of
+// generate_del_cluster / generate_ins_cluster (resolveINDEL.py:110-219, 319-432) in registers, one member per lane --
+// no shared-memory arena, ~3x fewer instructions than the general routine (core.h indel_cluster) and, as a kernel of its
+// own (k_cluster_small), a loop that stays inside the instruction cache (the general kernel spends most of its issue
+// slots waiting for instructions: 47 KB of hot code, 24 warps per SM at different places in it).
+//   exact duplicates / several signatures of one read: every lane looks at its peers (match.any on the read id); the
+//   lowest lane of a read carries the read's entry = its longest signature (first of equal length in (pos, len, input)
+//   order, resolveINDEL.py:125-131), ordered by the read's first occurrence (the dict order the stable sort by length
+//   keeps): sort key (len_best, pos_first, len_first, name).
+// 85 % of the kept clusters of 30x ONT have <= 32 members.
+// ------------------------------------------------------------------------------------------
+template <bool IS_INS>
+__device__ __forceinline__ void indel_cluster_small(const IndelView& in, int64_t s, int m, const ClusterParams& P, uint32_t kslot, const Emit& E) {
+    const int lane = (int)(threadIdx.x & 31);
+    const bool act = lane < m;
+    int32_t a = 0, len = 0, rid = -1 - lane, aux = 0;   // idle lanes: distinct negative ids
+    uint32_t idx = 0;
+    if (act) {
+        if (in.rec) {
+            const IndelRec r = in.rec[s + lane];
+            a = r.a; len = r.b; rid = r.rid; idx = r.idx;
+            if (IS_INS) aux = in.recc ? in.recc[s + lane] : 0;
+        } else {
+            idx = in.sidx[s + lane];
+            a = in.a[idx]; len = in.b[idx]; rid = in.rid[idx];
+            if (IS_INS) aux = in.c ? in.c[idx] : 0;
+        }
+    }
+    const int32_t pos = IS_INS ? (a >> 1) : a;
+    // the read's entry: best = its longest signature, first = its first occurrence in (pos, len, input index) order
+    int32_t len_b = len, pos_b = pos, aux_b = aux, pos_f = pos, len_f = len;
+    uint32_t idx_b = idx, idx_f = idx;
+    bool rep = act;
+    const uint32_t peers = __match_any_sync(0xffffffffu, rid);
+    if (__any_sync(0xffffffffu, peers != (1u << lane))) {
+        uint32_t rem = peers & ~(1u << lane);
+        while (__any_sync(0xffffffffu, rem != 0u)) {
+            const int j = rem ? __ffs(rem) - 1 : lane;
+            rem &= rem - 1u;
+            const int32_t pj = __shfl_sync(0xffffffffu, pos, j), lj = __shfl_sync(0xffffffffu, len, j), xj = __shfl_sync(0xffffffffu, aux, j);
+            const uint32_t ij = __shfl_sync(0xffffffffu, idx, j);
+            if (j != lane) {
+                if (pj < pos_f || (pj == pos_f && (lj < len_f || (lj == len_f && ij < idx_f)))) { pos_f = pj; len_f = lj; idx_f = ij; }
+                if (lj > len_b || (lj == len_b && (pj < pos_b || (pj == pos_b && ij < idx_b)))) { len_b = lj; pos_b = pj; aux_b = xj; idx_b = ij; }
+            }
+        }
+        rep = act && (int)(__ffs(peers) - 1) == lane;   // one lane per read
+    }
+    const uint32_t reps = __ballot_sync(0xffffffffu, rep);
+    const int u = __popc(reps);
+    if (u < P.min_support) {   // len(read_tag) < read_count (:133); (the signature-count test :62 is implied)
+        if (lane == 0) E.cnt[kslot] = 0;
+        return;
+    }
+    // bitonic sort of the reads by (len_best, pos_first, len_first, name), carrying the lane that holds the entry
+    uint64_t k0 = rep ? (((uint64_t)(uint32_t)len_b << 32) | (uint32_t)pos_f) : ~0ull;
+    uint64_t k1 = rep ? (((uint64_t)(uint32_t)len_f << 32) | (uint32_t)rid) : ~0ull;
+    int src = lane;
+#pragma unroll 1
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint64_t o0 = __shfl_xor_sync(0xffffffffu, k0, j), o1 = __shfl_xor_sync(0xffffffffu, k1, j);
+            const int os = __shfl_xor_sync(0xffffffffu, src, j);
+            const bool lower = (lane & j) == 0, up = (lane & k) == 0;
+            const bool gt = k0 > o0 || (k0 == o0 && k1 > o1);
+            const bool lt = k0 < o0 || (k0 == o0 && k1 < o1);
+            if ((lower == up) ? gt : lt) { k0 = o0; k1 = o1; src = os; }
+        }
+    }
+    // lane p < u now holds the read of sorted position p
+    const bool act_s = lane < u;
+    const int32_t len_s = (int32_t)(k0 >> 32), rid_s = (int32_t)(uint32_t)k1;
+    const int32_t pos_s = __shfl_sync(0xffffffffu, pos_b, src);
+    const int32_t aux_s = IS_INS ? __shfl_sync(0xffffffffu, aux_b, src) : 0;
+    const uint32_t idx_s = IS_INS ? __shfl_sync(0xffffffffu, idx_b, src) : 0u;
+    // allele split on the length-sorted reads (:137-162)
+    int64_t sum_len = act_s ? (int64_t)len_s : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum_len += __shfl_xor_sync(0xffffffffu, sum_len, o);
+    const double thr = P.ratio * ((double)sum_len / (double)u);
+    const int32_t len_prev = __shfl_up_sync(0xffffffffu, len_s, 1);
+    const bool brk = act_s && lane > 0 && (double)(len_s - len_prev) > thr;
+    const uint32_t B = __ballot_sync(0xffffffffu, brk) | 1u;     // bit p: an allele starts at sorted position p
+    const int na = __popc(B);
+    // alleles in (support, order) order = sorted(allele_collect, key=[support]) stable (:163): lane q < na owns allele q
+    int a_st = 0, a_n = 0, a_rank = 0;
+    if (lane < na) {
+        a_st = (int)__fns(B, 0, lane + 1);
+        const int a_en = lane + 1 < na ? (int)__fns(B, 0, lane + 2) : u;
+        a_n = a_en - a_st;
+    }
+    for (int q = 0; q < na; q++) {
+        const int nq = __shfl_sync(0xffffffffu, a_n, q);
+        if (lane < na && (nq < a_n || (nq == a_n && q < lane))) a_rank++;
+    }
+    uint32_t n_emit = 0;
+    const int32_t chrom = in.chrom[in.rec ? in.rec[s].idx : in.sidx[s]];
+    for (int k = 0; k < na; k++) {
+        const uint32_t who = __ballot_sync(0xffffffffu, lane < na && a_rank == k);
+        const int owner = __ffs(who) - 1;
+        const int st = __shfl_sync(0xffffffffu, a_st, owner), n = __shfl_sync(0xffffffffu, a_n, owner);
+        if (n < P.min_support_allele) continue;
+        const bool mem = lane >= st && lane < st + n;
+        int64_t sp = mem ? (int64_t)pos_s : 0, sl = mem ? (int64_t)len_s : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { sp += __shfl_xor_sync(0xffffffffu, sp, o); sl += __shfl_xor_sync(0xffffffffu, sl, o); }
+        int32_t pos_out, search, aux_out = 0;
+        if (IS_INS) {
+            // first member (allele order) whose sequence is long enough (:399-405); signalLen = sl / n (every member kept)
+            const int32_t need = (int32_t)((double)sl / (double)n);
+            const uint32_t okm = __ballot_sync(0xffffffffu, mem && aux_s >= need);
+            if (!okm) continue;   // ideal_ins_seq == '<INS>' -> dropped
+            const int pick = __ffs(okm) - 1;
+            pos_out = __shfl_sync(0xffffffffu, pos_s, pick);
+            aux_out = (int32_t)__shfl_sync(0xffffffffu, idx_s, pick);
+            search = pos_out;
+        } else {
+            // member closest to the mean position, index tie-break: |x - mean| ordered like |n*x - sum| (exact)
+            int64_t d = (int64_t)n * pos_s - sp;
+            if (d < 0) d = -d;
+            uint64_t key = mem ? (((uint64_t)d << 5) | (uint32_t)(lane - st)) : ~0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const uint64_t y = __shfl_xor_sync(0xffffffffu, key, o); if (y < key) key = y; }
+            search = __shfl_sync(0xffffffffu, pos_s, st + (int)(key & 31u));   // search_threshold (:177)
+            pos_out = (int32_t)((double)sp / (double)n);
+        }
+        uint32_t slot = 0, noff = 0;
+        if (lane == 0) emit_reserve_issue(E, (uint32_t)n, &slot, &noff);   // looked at after the std work
+        // CIPOS / CILEN: np.std over the allele (:191-194), lanes 0-7 pos / 8-15 len = numpy's eight strided accumulators
+        int32_t cipos, cilen;
+        {
+            const int which = (lane >> 3) & 1, j8 = lane & 7;
+            const double mean = (double)(which ? sl : sp) / (double)n;
+            auto sq = [&](int i) {
+                const int32_t v0 = __shfl_sync(0xffffffffu, pos_s, (st + i) & 31), v1 = __shfl_sync(0xffffffffu, len_s, (st + i) & 31);
+                const double x = (double)(which ? v1 : v0) - mean;
+                return x * x;
+            };
+            double res;
+            if (n < 8) {
+                res = 0.;
+                for (int i = 0; i < n; i++) res += sq(i);
+            } else {
+                const int n8 = n - (n % 8);
+                double r = sq(j8);
+                for (int i = 8 + j8; i < n8; i += 8) r += sq(i);
+                r = r + __shfl_xor_sync(0xffffffffu, r, 1);
+                r = r + __shfl_xor_sync(0xffffffffu, r, 2);
+                r = r + __shfl_xor_sync(0xffffffffu, r, 4);
+                res = r;
+                for (int i = n8; i < n; i++) res += sq(i);
+            }
+            res = res / (double)n;
+            const int32_t ci = cal_cipos(sqrt(res), n, E.pow_half);
+            cipos = __shfl_sync(0xffffffffu, ci, 0);
+            cilen = __shfl_sync(0xffffffffu, ci, 8);
+        }
+        int ok = 0;
+        if (lane == 0) {
+            note_support(E, (uint32_t)n);
+            ok = emit_reserve_check(E, (uint32_t)n, slot, noff) ? 1 : 0;
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        noff = __shfl_sync(0xffffffffu, noff, 0);
+        if (ok) {
+            if (mem) E.names[noff + (uint32_t)(lane - st)] = rid_s;
+            if (lane == 0) {
+                const double signalLen = (double)sl / (double)n;
+                csv_cand c;
+                c.svtype = IS_INS ? CSV_INS : CSV_DEL; c.chrom = chrom; c.pos = pos_out;
+                c.len = IS_INS ? (int32_t)signalLen : (int32_t)(-signalLen);
+                c.support = n; c.cipos = cipos; c.cilen = cilen; c.search_pos = search; c.pos2 = 0; c.aux = aux_out;
+                c.names_off = (int32_t)noff; c.names_cnt = n; c.cluster = (int32_t)kslot; c.flags = 0;
+                c.reserved[0] = (int32_t)n_emit; c.reserved[1] = 0;
+                E.cand[slot] = c;
+            }
+        }
+        n_emit++;
+    }
+    if (lane == 0) E.cnt[kslot] = n_emit;
+}
+
+// one warp per kept cluster of <= 32 members; larger ones are listed (rest_list) for the general kernel
+template <bool IS_INS>
+__global__ void __launch_bounds__(256) k_cluster_small(TypeJob J, Emit E, Counters* ctr, uint32_t* work, uint32_t* n_rest) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = job_n(J);
+    const uint32_t n_kept = ctr->n_kept[J.svtype];
+    uint32_t k_next = 0, n_done = 0, n_mem = 0;
+    if (lane == 0) k_next = atomicAdd(work, 1u);
+    while (true) {
+        const uint32_t k = __shfl_sync(0xffffffffu, k_next, 0);
+        if (k >= n_kept) break;
+        if (lane == 0) k_next = atomicAdd(work, 1u);
+        const int64_t s = J.kept_start[k];
+        const int m = cluster_size_warp(J, s, n, 32);
+        if (m > 32) {
+            if (lane == 0) {
+                const uint32_t o = atomicAdd(n_rest, 1u);
+                J.rest_list[o] = k;   // (capacity = kept capacity of the type)
+            }
+            continue;
+        }
+        indel_cluster_small<IS_INS>(J.iv, s, m, J.cp, J.kslot_base + k, E);
+        n_done++; n_mem += (uint32_t)m;
+    }
+    if (lane == 0) {
+        if (n_done) atomicAdd(&ctr->pad[0], n_done);
+        if (n_mem) atomicAdd(&ctr->n_members[J.svtype], n_mem);
+    }
+}
+
 // one warp per kept cluster; clusters larger than WARP_M are deferred to the CTA kernel
 template <int KIND>
 __global__ void __launch_bounds__(CL_THREADS) k_cluster_warp(TypeJob J, Emit E, Counters* ctr, uint32_t* work) {
@@ -766,17 +989,18 @@ __global__ void __launch_bounds__(CL_THREADS) k_cluster_warp(TypeJob J, Emit E, 
     char* arena = smem + (size_t)warp * (WARP_M * ARENA_PER_MAX);
     int64_t* red = (int64_t*)(smem + (size_t)WARPS * (WARP_M * ARENA_PER_MAX)) + warp * 40;
     const int64_t n = job_n(J);
-    const uint32_t n_kept = ctr->n_kept[J.svtype];
+    const uint32_t n_kept = J.rest_list ? *J.n_rest : ctr->n_kept[J.svtype];
     CudaTeam<32> tm;
     // dynamic hand-out (one atomic per cluster): cluster costs vary, a static stride leaves a long tail
     // (the ticket of the NEXT cluster is requested before the current one is processed, so the atomic's round
     //  trip overlaps the work)
-    uint32_t k_next = 0;
+    uint32_t k_next = 0, n_mem = 0;
     if (lane == 0) k_next = atomicAdd(work, 1u);
     while (true) {
-        const uint32_t k = __shfl_sync(0xffffffffu, k_next, 0);
-        if (k >= n_kept) break;
+        const uint32_t q = __shfl_sync(0xffffffffu, k_next, 0);
+        if (q >= n_kept) break;
         if (lane == 0) k_next = atomicAdd(work, 1u);
+        const uint32_t k = J.rest_list ? J.rest_list[q] : q;   // after k_cluster_small: only the clusters it left
         const int64_t s = J.kept_start[k];
         const int m = cluster_size_warp(J, s, n, WARP_M);
         if (m > WARP_M) {
@@ -786,10 +1010,11 @@ __global__ void __launch_bounds__(CL_THREADS) k_cluster_warp(TypeJob J, Emit E, 
             }
             continue;
         }
-        if (lane == 0) atomicAdd(&ctr->n_members[J.svtype], (uint32_t)m);
+        n_mem += (uint32_t)m;
         run_cluster<KIND>(tm, J, s, m, pow2ceil(m), arena, red, J.kslot_base + k, E);
         __syncwarp();
     }
+    if (lane == 0 && n_mem) atomicAdd(&ctr->n_members[J.svtype], n_mem);
 }
 
 // size of the chain cluster starting at s (CTA-cooperative, exact)
@@ -869,9 +1094,11 @@ __device__ __forceinline__ uint32_t window_bin(const GenoJob& G, const csv_cand&
 }
 
 // candidates into the reference's emission order; when genotyping, the same pass counts the genotype windows per bin
-__global__ void k_permute(const csv_cand* __restrict__ tmp, const uint32_t* __restrict__ base, const Counters* ctr, uint32_t cap,
-                          csv_cand* __restrict__ out, GenoJob G) {
-    const uint32_t n = min(ctr->n_cand, cap);
+__global__ void k_permute(const csv_cand* __restrict__ tmp, const uint32_t* __restrict__ base, Counters* ctr, uint32_t cap,
+                          csv_cand* __restrict__ out, GenoJob G, const unsigned long long* cursor) {
+    const unsigned long long cur = *cursor;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->n_cand = (uint32_t)(cur >> 32); ctr->n_names = (uint32_t)cur; }   // for the kernels after this one
+    const uint32_t n = min((uint32_t)(cur >> 32), cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         csv_cand c = tmp[i];
         const uint32_t dst = base[c.cluster] + (uint32_t)c.reserved[0];
@@ -982,7 +1209,13 @@ __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const
                                                     const int32_t* __restrict__ r_id, const uint8_t* __restrict__ r_prim,
                                                     int64_t n_reads, uint32_t* status) {
     constexpr int ITEMS = 4;
+    constexpr int TAB = 1024;            // contigs whose (offset, validity) live in shared memory
     __shared__ uint32_t s_warp[10];
+    __shared__ uint64_t s_off[TAB];      // linear offset, ~0 for a contig outside the shard
+    __shared__ uint8_t s_seen[TAB];
+    const int n_tab = G.ct.n < TAB ? G.ct.n : TAB;
+    for (int i = threadIdx.x; i < n_tab; i += 256) { s_off[i] = G.ct.len[i] < 0 ? ~0ull : G.ct.off[i]; s_seen[i] = 0; }
+    __syncthreads();
     const int64_t n_tiles = (n_reads + 256 * ITEMS - 1) / (256 * ITEMS);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * 256 * ITEMS;
@@ -992,7 +1225,8 @@ __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const
         for (int j = 0; j < ITEMS; j++) {
             const int64_t r = base + j * 256 + threadIdx.x;
             const bool in = r < n_reads;
-            ch[j] = in ? r_chrom[r] : -1; st[j] = in ? r_start[r] : 0; en[j] = in ? r_end[r] : 0; pr[j] = in ? r_prim[r] : 0;
+            ch[j] = in ? __ldcs(r_chrom + r) : -1; st[j] = in ? __ldcs(r_start + r) : 0; en[j] = in ? __ldcs(r_end + r) : 0;
+            pr[j] = in ? __ldcs(r_prim + r) : 0;
         }
         uint32_t w[ITEMS], cnt[ITEMS], total = 0;
         uint64_t lin[ITEMS];   // RS of the read
@@ -1001,24 +1235,32 @@ __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const
             w[j] = 0; cnt[j] = 0; lin[j] = 0;
             const int64_t r = base + j * 256 + threadIdx.x;
             if (r >= n_reads) continue;
-            if (ch[j] < 0 || ch[j] >= G.ct.n || G.ct.len[ch[j]] < 0) { atomicOr(status, ST_BAD_CHROM); continue; }   // len < 0: outside the shard
-            if (!G.has_rows[ch[j]]) G.has_rows[ch[j]] = 1;
+            if (ch[j] < 0 || ch[j] >= G.ct.n) { atomicOr(status, ST_BAD_CHROM); continue; }
+            uint64_t off;
+            if (ch[j] < TAB) {
+                off = s_off[ch[j]];
+                if (!s_seen[ch[j]]) s_seen[ch[j]] = 1;
+            } else {
+                off = G.ct.len[ch[j]] < 0 ? ~0ull : G.ct.off[ch[j]];
+                if (!G.has_rows[ch[j]]) G.has_rows[ch[j]] = 1;
+            }
+            if (off == ~0ull) { atomicOr(status, ST_BAD_CHROM); continue; }   // outside the shard
             if (!pr[j]) continue;
-            const uint64_t off = G.ct.off[ch[j]];
             const uint64_t RS = off + (uint64_t)(uint32_t)st[j], RE = off + (uint64_t)(uint32_t)en[j];
             lin[j] = RS;
             const uint32_t b0 = (uint32_t)(RS >> G.shift);
             uint32_t b1 = (uint32_t)(RE >> G.shift);
             if (b1 >= G.n_bins) b1 = G.n_bins - 1;
             if (b0 > b1) continue;
-            bool any = false;
-            for (uint32_t wi = b0 >> 5; wi <= (b1 >> 5) && !any; wi++) {
-                uint32_t m = __ldg(&G.bin_bits[wi]);
-                if (wi == (b0 >> 5)) m &= 0xffffffffu << (b0 & 31);
-                if (wi == (b1 >> 5)) m &= 0xffffffffu >> (31 - (b1 & 31));
-                any = m != 0;
+            // any occupied bin in [b0, b1]?  One or two words of the bit map for a typical read.
+            const uint32_t w0 = b0 >> 5, w1 = b1 >> 5;
+            uint32_t m = __ldg(&G.bin_bits[w0]) & (0xffffffffu << (b0 & 31));
+            if (w1 == w0) m &= 0xffffffffu >> (31 - (b1 & 31));
+            else {
+                for (uint32_t wi = w0 + 1; wi < w1 && !m; wi++) m = __ldg(&G.bin_bits[wi]);
+                if (!m) m = __ldg(&G.bin_bits[w1]) & (0xffffffffu >> (31 - (b1 & 31)));
             }
-            if (any) { w[j] = G.bin_start[b0]; cnt[j] = G.bin_start[b1 + 1] - w[j]; total += cnt[j]; }
+            if (m) { w[j] = G.bin_start[b0]; cnt[j] = G.bin_start[b1 + 1] - w[j]; total += cnt[j]; }
         }
         uint32_t o = block_reserve_256(total, PB.count, s_warp);
 #pragma unroll
@@ -1041,6 +1283,9 @@ __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const
             o += cnt[j];
         }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_tab; i += 256)
+        if (s_seen[i] && !G.has_rows[i]) G.has_rows[i] = 1;
 }
 
 template <bool LIN32>

@@ -171,7 +171,7 @@ class Engine(object):
         v = list(out)
         t = _abi.TYPE_NAMES
         return dict(status=v[0], n_cand=v[1], n_names=v[2], max_support=v[3], kept=dict(zip(t, v[4:9])), big=dict(zip(t, v[9:14])),
-                    giant=dict(zip(t, v[14:19])), pairs=v[19], domain=dict(zip(t, v[20:25])), members=dict(zip(t, v[25:30])))
+                    giant=dict(zip(t, v[14:19])), pairs=v[19], domain=dict(zip(t, v[20:25])), members=dict(zip(t, v[25:30])), small_path=v[30])
 
     def kernel_times(self):
         """{kernel name: (launches, total ms)} of the calls made while profiling was on (collected by fetch())."""

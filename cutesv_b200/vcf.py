@@ -208,6 +208,27 @@ class IndexedFasta(object):
         self.entries = {}
         self.full = None
         fai = path + ".fai"
+        with open(path, "rb") as f:
+            magic = f.read(2)
+        if magic == b"\x1f\x8b":
+            # gzip / bgzip reference (pysam.FastaFile reads .fa.gz through its .gzi): the .fai offsets address the
+            # UNcompressed stream, so decompress once instead of seeking into compressed bytes
+            import gzip
+            import io
+            self.full = {}
+            name, chunks = None, []
+            with gzip.open(path, "rb") as g:
+                for line in io.BufferedReader(g):
+                    if line.startswith(b">"):
+                        if name is not None:
+                            self.full[name] = b"".join(chunks).decode()
+                        name, chunks = line[1:].split()[0].decode(), []
+                    elif name is not None:
+                        chunks.append(line.strip())
+            if name is not None:
+                self.full[name] = b"".join(chunks).decode()
+            self.fh = None
+            return
         if os.path.exists(fai):
             with open(fai) as f:
                 for line in f:

@@ -76,38 +76,74 @@ def name_index(*tuple_lists_and_fields):
     """Rank of every read name in Python string order over several (list, field index) pairs."""
     names = set()
     for lst, k in tuple_lists_and_fields:
-        for t in lst:
-            names.add(t[k])
+        if lst:
+            names.update(list(zip(*lst))[k])
     ordered = sorted(names)
     return {n: i for i, n in enumerate(ordered)}, ordered
 
 
+def _ids(values, index):
+    return np.fromiter(map(index.__getitem__, values), dtype=np.int32, count=len(values))
+
+
 def tuples_to_columns(svtype, tuples, chrom_id, name_id):
+    """Reference tuples -> int32 columns, column-wise (zip(*tuples) transposes at C speed; no per-tuple Python loop)."""
     n = len(tuples)
     cols = dict(chrom=np.zeros(n, np.int32), a=np.zeros(n, np.int32), b=np.zeros(n, np.int32), read_id=np.zeros(n, np.int32),
                 c=np.zeros(n, np.int32) if svtype in ("INS", "INV", "TRA") else None)
-    for i, t in enumerate(tuples):
-        cols["chrom"][i] = chrom_id[t[-1]]
-        if svtype == "DEL" or svtype == "DUP":
-            cols["a"][i], cols["b"][i], cols["read_id"][i] = int(t[0]), int(t[1]), name_id[t[2]]
-        elif svtype == "INS":
-            cols["a"][i] = int(round(float(t[0]) * 2))  # positions from split reads can be x.5 (cuteSV:228,244)
-            cols["b"][i], cols["read_id"][i], cols["c"][i] = int(t[1]), name_id[t[2]], len(t[3])
-        elif svtype == "INV":
-            cols["c"][i] = 0 if t[0] == "++" else 1
-            cols["a"][i], cols["b"][i], cols["read_id"][i] = int(t[1]), int(t[2]), name_id[t[3]]
-        elif svtype == "TRA":
-            cols["a"][i], cols["b"][i], cols["read_id"][i] = int(t[1]), int(t[3]), name_id[t[4]]
-            cols["c"][i] = chrom_id[t[2]] * 4 + _TRA[t[0]]
+    if n == 0:
+        return cols
+    f = list(zip(*tuples))
+    cols["chrom"] = _ids(f[-1], chrom_id)
+    if svtype == "DEL" or svtype == "DUP":
+        cols["a"] = np.asarray(f[0], dtype=np.float64).astype(np.int32)   # int(): truncation
+        cols["b"] = np.asarray(f[1], dtype=np.float64).astype(np.int32)
+        cols["read_id"] = _ids(f[2], name_id)
+    elif svtype == "INS":
+        cols["a"] = np.rint(np.asarray(f[0], dtype=np.float64) * 2).astype(np.int32)  # positions from split reads can be x.5 (cuteSV:228,244)
+        cols["b"] = np.asarray(f[1], dtype=np.int64).astype(np.int32)
+        cols["read_id"] = _ids(f[2], name_id)
+        cols["c"] = np.fromiter(map(len, f[3]), dtype=np.int32, count=n)
+    elif svtype == "INV":
+        cols["c"] = np.fromiter((0 if x == "++" else 1 for x in f[0]), dtype=np.int32, count=n)
+        cols["a"] = np.asarray(f[1], dtype=np.float64).astype(np.int32)
+        cols["b"] = np.asarray(f[2], dtype=np.float64).astype(np.int32)
+        cols["read_id"] = _ids(f[3], name_id)
+    elif svtype == "TRA":
+        cols["a"] = np.asarray(f[1], dtype=np.float64).astype(np.int32)
+        cols["b"] = np.asarray(f[3], dtype=np.float64).astype(np.int32)
+        cols["read_id"] = _ids(f[4], name_id)
+        cols["c"] = _ids(f[2], chrom_id) * 4 + np.fromiter(map(_TRA.__getitem__, f[0]), dtype=np.int32, count=n)
     return cols
 
 
 def reads_to_columns(rows, chrom_id, name_id):
     n = len(rows)
-    out = dict(chrom=np.zeros(n, np.int32), start=np.zeros(n, np.int32), end=np.zeros(n, np.int32), read_id=np.zeros(n, np.int32),
-               is_primary=np.zeros(n, np.uint8))
-    for i, r in enumerate(rows):
-        out["start"][i], out["end"][i], out["is_primary"][i] = r[0], r[1], r[2]
-        out["read_id"][i] = name_id[r[3]]
-        out["chrom"][i] = chrom_id[r[4]]
-    return out
+    if n == 0:
+        return dict(chrom=np.zeros(0, np.int32), start=np.zeros(0, np.int32), end=np.zeros(0, np.int32), read_id=np.zeros(0, np.int32),
+                    is_primary=np.zeros(0, np.uint8))
+    f = list(zip(*rows))
+    return dict(chrom=_ids(f[4], chrom_id), start=np.asarray(f[0], dtype=np.int64).astype(np.int32),
+                end=np.asarray(f[1], dtype=np.int64).astype(np.int32), read_id=_ids(f[3], name_id),
+                is_primary=np.asarray(f[2], dtype=np.int64).astype(np.uint8))
+
+
+def columns_to_tuples(svtype, cols, chrom_names, read_names, ins_seq=None):
+    """int32 columns -> the reference's tuple lists (--retain_work_dir), column-wise."""
+    n = len(cols["chrom"])
+    if n == 0:
+        return []
+    ch = [chrom_names[i] for i in cols["chrom"].tolist()]
+    nm = [read_names[i] for i in cols["read_id"].tolist()]
+    a, b = cols["a"].tolist(), cols["b"].tolist()
+    if svtype == "DEL" or svtype == "DUP":
+        return list(zip(a, b, nm, [svtype] * n, ch))
+    if svtype == "INS":
+        pos = [(x // 2 if x % 2 == 0 else x / 2) for x in a]
+        return list(zip(pos, b, nm, ins_seq, ["INS"] * n, ch))
+    c = cols["c"].tolist()
+    if svtype == "INV":
+        return list(zip([("++" if x == 0 else "--") for x in c], a, b, nm, ["INV"] * n, ch))
+    if svtype == "TRA":
+        return list(zip(["ABCD"[x & 3] for x in c], a, [chrom_names[x >> 2] for x in c], b, nm, ["TRA"] * n, ch))
+    raise ValueError(svtype)

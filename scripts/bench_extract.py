@@ -13,8 +13,9 @@ import numpy as np
 from cutesv_b200 import _abi, synth
 from cutesv_b200.engine import Engine
 
-n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
-pk, names, lens = synth.synth_cigar_packet(n_reads)
+n_reads = int(sys.argv[1]) if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else 200000
+mean_indels = int(sys.argv[2]) if len(sys.argv) > 2 and not sys.argv[2].startswith("-") else 850
+pk, names, lens = synth.synth_cigar_packet(n_reads, mean_indels=mean_indels, sa_frac=0.2 if mean_indels > 2000 else 0.0)
 p = _abi.default_params()
 e = Engine(0, params=p, contig_lens=lens)
 e.set_profiling(True)
@@ -28,7 +29,7 @@ for _ in range(10):
     wall.append(time.perf_counter() - t0)
     ms.append(e.stage_ms()["extract"])
 n_ops = len(pk["cigar"])
-alg = 4.0 * n_ops + 44.0 * n_reads
+alg = 4.0 * n_ops + 44.0 * n_reads + 28.0 * len(pk["sa"]["chrom"])
 peak = 6482.7
 try:
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])

@@ -15,7 +15,16 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def engine():
+    """One csv_ctx on cuda:0 for the whole session.  Without a usable B200 the tests that need it are SKIPPED (the library
+    itself never falls back: csv_create fails with CSV_E_NODEVICE)."""
+    from cutesv_b200 import _abi
+    from cutesv_b200._lib import CuteSVError
     from cutesv_b200.engine import Engine
-    e = Engine(0)
+    try:
+        e = Engine(0)
+    except CuteSVError as err:
+        if err.code == _abi.CSV_E_NODEVICE:
+            pytest.skip("no usable sm_100 device: %s" % err)
+        raise
     yield e
     e.close()

@@ -42,6 +42,7 @@ Emit make_emit(Ctx& c) {
     E.pow_half = c.pow_half.data();
     E.lim.cap_cand = (uint32_t)c.cand_tmp.size(); E.lim.cap_names = (uint32_t)c.names.size();
     E.lim.pow_n = (uint32_t)c.pow_half.size();
+    E.cursor = nullptr;
     return E;
 }
 

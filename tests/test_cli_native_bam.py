@@ -151,3 +151,34 @@ def test_cli_ins_ties_ordered_by_sequence_cpu(tmp_path, monkeypatch):
 def test_cli_ins_ties_ordered_by_sequence_gpu(engine, tmp_path):
     lines, gold = _run_ties(engine, tmp_path)
     assert lines == gold
+
+
+def test_write_old_sigs_content(tmp_path):
+    """--retain_work_dir --write_old_sigs: the legacy text dumps (cuteSV:766-816) hold exactly the de-duplicated signatures of
+    the pickles, sorted by the reference's keys, one tab-separated line each."""
+    import pickle as pk
+    from emul_engine import EmulEngine
+    lines, gold, wd = _run(EmulEngine(), tmp_path, 1, ["--retain_work_dir", "--write_old_sigs"])
+    assert lines == gold
+    idx = pk.load(open(os.path.join(wd, "sigindex.pickle"), "rb"))
+    n_checked = 0
+    for t, nf in (("DEL", 5), ("INS", 6), ("DUP", 5), ("INV", 6), ("TRA", 7)):
+        rows = []
+        with open(os.path.join(wd, t + ".pickle"), "rb") as f:
+            for chrom in sorted(idx[t], key=lambda c: idx[t][c]):
+                f.seek(idx[t][chrom])
+                rows.extend(pk.load(f))
+        text = [l.rstrip("\n").split("\t") for l in open(os.path.join(wd, t + ".sigs"))]
+        assert len(text) == len(rows), t
+        for e, l in zip(rows, text):
+            assert len(l) == nf and l[0] == e[-2] and l[1] == e[-1], (t, l)
+            if t in ("DEL", "DUP"):
+                assert (int(l[2]), int(l[3]), l[4]) == (int(e[0]), int(e[1]), e[2])
+            elif t == "INS":
+                assert (int(l[2]), int(l[3]), l[4], l[5]) == (int(e[0]), int(e[1]), e[2], e[3])
+            elif t == "INV":
+                assert (l[2], int(l[3]), int(l[4]), l[5]) == (e[0], int(e[1]), int(e[2]), e[3])
+            else:
+                assert (l[2], int(l[3]), l[4], int(l[5]), l[6]) == (e[0], int(e[1]), e[2], int(e[3]), e[4])
+            n_checked += 1
+    assert n_checked > 200
