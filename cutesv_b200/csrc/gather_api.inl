@@ -86,15 +86,21 @@ extern "C" int csv_comm_destroy(csv_ctx* c) {
 
 // ---- message of one rank: header | pad_cand x csv_cand | pad_cand x csv_geno | pad_names x int32 ----
 static constexpr int64_t GH_WORDS = 4;   // header: n_cand, n_names, overflow, rank (int64 each)
+static constexpr int GM_MAX_KEYS = 2048; // (svtype, contig) groups the merge handles through a shared-memory table
 struct GatherLayout {
-    int64_t pad_cand, pad_names, off_geno, off_names, msg_bytes;
+    int64_t pad_cand, pad_names, off_geno, off_names, off_tab, msg_bytes;
+    int32_t n_keys;   // 5 * n_contigs when <= GM_MAX_KEYS, else 0 (binary-search merge)
 };
-static GatherLayout gather_layout(int64_t pad_cand, int64_t pad_names) {
+// message of one rank: header | pad_cand x csv_cand | pad_cand x csv_geno | pad_names x int32 | n_keys x (first, count)
+static GatherLayout gather_layout(int64_t pad_cand, int64_t pad_names, int32_t n_contigs, int world) {
     GatherLayout L;
     L.pad_cand = pad_cand; L.pad_names = pad_names;
+    L.n_keys = CSV_NTYPES * n_contigs <= GM_MAX_KEYS ? CSV_NTYPES * n_contigs : 0;
+    if ((size_t)L.n_keys * (world + 1) * 4 > 160 * 1024) L.n_keys = 0;   // the merge keeps (world + 1) words per key in shared memory
     L.off_geno = GH_WORDS * 8 + pad_cand * (int64_t)sizeof(csv_cand);
     L.off_names = L.off_geno + pad_cand * (int64_t)sizeof(csv_geno);
-    L.msg_bytes = (L.off_names + pad_names * 4 + 15) / 16 * 16;
+    L.off_tab = (L.off_names + pad_names * 4 + 15) / 16 * 16;
+    L.msg_bytes = (L.off_tab + (int64_t)L.n_keys * 8 + 15) / 16 * 16;
     return L;
 }
 
@@ -112,6 +118,17 @@ __global__ void __launch_bounds__(256) k_gather_pack(const csv_cand* __restrict_
     const uint4* src_c = (const uint4*)cand;
     uint4* dst_c = (uint4*)(msg + GH_WORDS * 8);
     for (int64_t i = tid; i < cc * 4; i += stride) dst_c[i] = src_c[i];
+    if (L.n_keys) {   // (first record, count) of every (svtype, contig) group of this rank: the records are sorted by that key
+        uint2* tab = (uint2*)(msg + L.off_tab);   // zeroed before this kernel
+        const int32_t nct = L.n_keys / CSV_NTYPES;
+        for (int64_t i = tid; i < cc; i += stride) {
+            const int32_t sv = cand[i].svtype, ch = cand[i].chrom;
+            if (sv < 0 || sv >= CSV_NTYPES || ch < 0 || ch >= nct) continue;
+            const int32_t k = sv * nct + ch;
+            if (i == 0 || cand[i - 1].svtype != sv || cand[i - 1].chrom != ch) tab[k].x = (uint32_t)i;
+            if (i + 1 == cc || cand[i + 1].svtype != sv || cand[i + 1].chrom != ch) tab[k].y = (uint32_t)(i + 1);   // end; count = end - first
+        }
+    }
     const uint2* src_g = (const uint2*)geno;
     uint2* dst_g = (uint2*)(msg + L.off_geno);
     for (int64_t i = tid; i < cc * 5; i += stride) dst_g[i] = src_g[i];
@@ -147,10 +164,60 @@ __device__ __forceinline__ int64_t gm_bound(const MergeJob& M, int r, int64_t k)
     return lo;
 }
 __global__ void __launch_bounds__(256) k_gather_merge(MergeJob M) {
+    extern __shared__ uint32_t s_gm[];   // table path: [n_keys] exclusive offset of every key group, then [world * n_keys] of every (rank, key)
+    __shared__ uint32_t s_warp[9];
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     if (tid < (int64_t)M.world * GH_WORDS) M.hdr[tid] = gm_header(M, (int)(tid / GH_WORDS))[tid % GH_WORDS];
     const int64_t per = M.L.pad_cand, total = per * M.world;
-    for (int64_t g = tid; g < total; g += stride) {
+    const int T = M.L.n_keys;
+    if (T) {
+        // merged position of a record = (records of all ranks with a smaller key) + (records of lower ranks with the same key)
+        // + its offset inside its own group: O(1) per record from the (first, end) tables every message carries
+        uint32_t* s_key = s_gm;            // [T]
+        uint32_t* s_rk = s_gm + T;         // [world * T]
+        constexpr int PER = GM_MAX_KEYS / 256;
+        uint32_t loc[PER], sum = 0;
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const int k = threadIdx.x * PER + j;
+            uint32_t t = 0;
+            if (k < T)
+                for (int r = 0; r < M.world; r++) {
+                    const uint2 e = ((const uint2*)(M.recv + (int64_t)r * M.L.msg_bytes + M.L.off_tab))[k];
+                    s_rk[r * T + k] = t;   // records of lower ranks with this key
+                    t += e.y - e.x;
+                }
+            loc[j] = t; sum += t;
+        }
+        uint32_t tot;
+        uint32_t run = block_excl_scan_256(sum, s_warp, &tot);
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const int k = threadIdx.x * PER + j;
+            if (k < T) s_key[k] = run;
+            run += loc[j];
+        }
+        __syncthreads();
+        const int32_t nct = T / CSV_NTYPES;
+        for (int64_t g = tid; g < total; g += stride) {
+            const int r = (int)(g / per);
+            const int64_t i = g - (int64_t)r * per;
+            if (i >= gm_valid(M, r)) continue;
+            const char* msg = M.recv + (int64_t)r * M.L.msg_bytes;
+            csv_cand c = ((const csv_cand*)(msg + GH_WORDS * 8))[i];
+            if (c.svtype < 0 || c.svtype >= CSV_NTYPES || c.chrom < 0 || c.chrom >= nct) { M.hdr[M.world * GH_WORDS] = 1; continue; }
+            const int k = c.svtype * nct + c.chrom;
+            const uint32_t first = ((const uint2*)(msg + M.L.off_tab))[k].x;
+            const int64_t dst = (int64_t)s_key[k] + s_rk[r * T + k] + (i - (int64_t)first);
+            int64_t nbase = 0;
+            for (int q = 0; q < r; q++) nbase += gm_header(M, q)[1];
+            c.names_off += (int32_t)nbase;
+            c.reserved[1] = r;
+            if (dst < M.cap_c) { M.out_c[dst] = c; M.out_g[dst] = ((const csv_geno*)(msg + M.L.off_geno))[i]; }
+            else M.hdr[M.world * GH_WORDS] = 2;
+        }
+    } else
+    for (int64_t g = tid; g < total; g += stride) {   // many contigs: binary searches over the other ranks' records
         const int r = (int)(g / per);
         const int64_t i = g - (int64_t)r * per;
         if (i >= gm_valid(M, r)) continue;
@@ -181,7 +248,7 @@ __global__ void __launch_bounds__(256) k_gather_merge(MergeJob M) {
 }
 
 static int gather_enqueue(csv_ctx* c) {
-    const GatherLayout L = gather_layout(c->pad_cand, c->pad_names);
+    const GatherLayout L = gather_layout(c->pad_cand, c->pad_names, c->n_contigs, c->world);
     const int W = c->world;
     CU(c->g_send.ensure((size_t)L.msg_bytes));
     CU(c->g_recv.ensure((size_t)L.msg_bytes * W));
@@ -190,6 +257,7 @@ static int gather_enqueue(csv_ctx* c) {
     CU(c->g_geno.ensure((size_t)L.pad_cand * W * sizeof(csv_geno) + 64));
     CU(c->g_names.ensure((size_t)L.pad_names * W * 4 + 64));
     // pack -> ONE ncclAllGather -> merge: three launches and one small D2H copy per step
+    if (L.n_keys) CU(cudaMemsetAsync(c->g_send.as<char>() + L.off_tab, 0, (size_t)L.n_keys * 8, c->stream));
     LAUNCH(c, k_gather_pack, c->n_sm * 2, 256, 0, c->cand.as<csv_cand>(), c->geno.as<csv_geno>(), c->names.as<int32_t>(),
            c->counters.as<Counters>(), c->cap_cand, c->cap_names, L, c->rank, c->g_send.as<char>());
     NC(g_nccl.AllGather(c->g_send.p, c->g_recv.p, (size_t)L.msg_bytes, ncclUint8, c->comm, c->stream));
@@ -198,7 +266,9 @@ static int gather_enqueue(csv_ctx* c) {
     M.out_c = c->g_cand.as<csv_cand>(); M.out_g = c->g_geno.as<csv_geno>(); M.out_n = c->g_names.as<int32_t>();
     M.cap_c = L.pad_cand * W; M.cap_n = L.pad_names * W;
     M.hdr = c->g_scratch.as<int64_t>();
-    LAUNCH(c, k_gather_merge, grid_for(c, std::max<int64_t>(L.pad_cand * W, L.pad_names), 256, 4), 256, 0, M);
+    const size_t gm_smem = (size_t)L.n_keys * (W + 1) * 4;
+    if (gm_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_gather_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm_smem));
+    LAUNCH(c, k_gather_merge, grid_for(c, std::max<int64_t>(L.pad_cand * W, L.pad_names), 256, 2), 256, gm_smem, M);
     CU(cudaMemcpyAsync(c->h_gather, M.hdr, (size_t)(W * GH_WORDS + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     c->gathered = true;
     return CSV_OK;

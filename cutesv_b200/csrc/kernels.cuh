@@ -10,6 +10,7 @@
 #include "core.h"
 #include "devprims.cuh"
 #include "radix.cuh"
+#include <type_traits>
 
 namespace csv {
 
