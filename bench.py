@@ -190,16 +190,21 @@ def strip(d):
 # filter, M members of kept chain clusters, R reads rows, C candidates, P (read, window) pairs, B histogram buckets ----
 def kernel_bytes(name, q):
     n, S, M, R, C, P, B = q["n"], q["S"], q["M"], q["R"], q["C"], q["P"], q["B"]
+    rec = 22.0 * M + 64.0 * C + 4.0 * M     # 16 B record (+ 4 B c of INS) per member read, 64 B row + read ids written
     table = {
         "k_indel_hist": 8.0 * n,
-        "k_bucket_prefix": 8.0 * B,
+        "k_bucket_prefix<1>": 8.0 * B, "k_bucket_prefix<2>": 8.0 * B, "k_bucket_prefix<3>": 8.0 * B, "k_bucket_prefix<4>": 8.0 * B,
+        "k_bucket_prefix<5>": 8.0 * B, "k_bucket_prefix<6>": 8.0 * B, "k_bucket_prefix<7>": 8.0 * B, "k_bucket_prefix<8>": 8.0 * B,
+        "k_bucket_prefix<0>": 8.0 * B,
         "k_indel_scatter": 8.0 * n + 8.0 * S,
         "k_bucket_fixup": 16.0 * S + 4.0 * B,
-        "k_member_records": 8.0 * S + 36.0 * M,
-        "k_select_heads": 4.0 * S,
-        "k_cluster_warp<INDEL>": 22.0 * M + 64.0 * C + 4.0 * M,
-        "k_reads_pass": 17.0 * R,
-        "k_pairs_test": 16.0 * P,
+        "k_select_heads": 4.0 * S + 36.0 * M,
+        # the register kernel takes the clusters of <= 32 members (~85 % of the members), the general kernel the rest
+        "k_cluster_small<DEL>": 0.85 * rec, "k_cluster_small<INS>": 0.85 * rec,
+        "k_cluster_warp<DEL,keep-all>": 0.15 * rec, "k_cluster_warp<INS,keep-all>": 0.15 * rec,
+        "k_cluster_warp<DEL>": rec, "k_cluster_warp<INS>": rec, "k_cluster_warp<INDEL>": rec,
+        "k_reads_pass<true>": 17.0 * R, "k_reads_pass<false>": 17.0 * R,
+        "k_pairs_test<true>": 48.0 * P, "k_pairs_test<false>": 16.0 * P,
         "k_indel_keys<uint32_t, true>": 20.0 * n,
         "k_indel_keys<uint32_t, false>": 20.0 * n,
         "k_prefilter": 4.0 * n + 8.0 * S,

@@ -164,6 +164,8 @@ struct csv_ctx {
     DBuf d_goff[CSV_NTYPES + 1];   // contig row offsets of grouped uploads (last: reads table)
     LaneWork lanes[N_LANES - 1];   // lane 0 = the ctx's own stream and buffers
     cudaEvent_t ev_fork = nullptr;
+    cudaStream_t side_stream[2] = {nullptr, nullptr};   // DEL / INS: the general cluster kernels beside the register kernel
+    cudaEvent_t ev_side_fork[2] = {nullptr, nullptr}, ev_side_join[2] = {nullptr, nullptr};
     cudaStream_t aux_stream = nullptr;   // resets of the genotype stage's scratch run beside the lanes
     cudaEvent_t ev_aux = nullptr;
     bool lanes_enabled = true;
@@ -212,6 +214,16 @@ struct csv_ctx {
     uint64_t cfg_epoch = 1, graph_clock = 0;   // cfg_epoch: bumped by csv_set_contigs / csv_set_shard
     int64_t graph_replays = 0;
     // multi-GPU (csv_comm_init / csv_allgather)
+    struct P2PState {
+        bool ready = false, failed = false;
+        void* box = nullptr;              // this rank's mail box: 2 buffers x world slots, then 2 x world arrival flags
+        int64_t slot_bytes = 0;
+        size_t flags_off = 0;
+        std::vector<void*> peer;          // every rank's box as mapped here (CUDA IPC)
+        DBuf d_tab;                       // device tables of slot / flag pointers + the push kernel's done counter
+        unsigned long long epoch = 0;
+    } p2p;
+    bool p2p_enabled = true;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     DBuf g_send, g_recv, g_cand, g_geno, g_names, g_scratch;
@@ -376,6 +388,11 @@ extern "C" int csv_create(int device, void* stream, csv_ctx** out) {
         if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
         if (e4 == cudaSuccess) e4 = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
         if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming);
+        for (int k = 0; k < 2 && e4 == cudaSuccess; k++) {
+            e4 = cudaStreamCreateWithFlags(&c->side_stream[k], cudaStreamNonBlocking);
+            if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->ev_side_fork[k], cudaEventDisableTiming);
+            if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->ev_side_join[k], cudaEventDisableTiming);
+        }
         for (int l = 0; l < N_LANES - 1 && e4 == cudaSuccess; l++) {
             e4 = cudaStreamCreateWithFlags(&c->lanes[l].stream, cudaStreamNonBlocking);
             if (e4 == cudaSuccess) e4 = cudaEventCreateWithFlags(&c->lanes[l].ev_join, cudaEventDisableTiming);
@@ -387,6 +404,7 @@ extern "C" int csv_create(int device, void* stream, csv_ctx** out) {
     if (const char* e = getenv("CUTESV_B200_NO_PREFILTER")) c->prefilter_enabled = atoi(e) == 0;
     if (const char* e = getenv("CUTESV_B200_LANES")) c->lanes_enabled = atoi(e) != 0;
     if (const char* e = getenv("CUTESV_B200_GRAPHS")) c->graphs_enabled = atoi(e) != 0;
+    if (const char* e = getenv("CUTESV_B200_GATHER")) c->p2p_enabled = strcmp(e, "nccl") != 0;
     if (const char* e = getenv("CUTESV_B200_BUCKET_SORT")) c->bucket_sort_enabled = atoi(e) != 0;
     if (const char* e = getenv("CUTESV_B200_RECORDS")) c->records_enabled = atoi(e) != 0;
     if (const char* e = getenv("CUTESV_B200_SMALL_PATH")) c->small_path_enabled = atoi(e) != 0;
@@ -445,6 +463,11 @@ extern "C" int csv_destroy(csv_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); }
     if (c->ev_aux) cudaEventDestroy(c->ev_aux);
+    for (int k = 0; k < 2; k++) {
+        if (c->side_stream[k]) { cudaStreamSynchronize(c->side_stream[k]); cudaStreamDestroy(c->side_stream[k]); }
+        if (c->ev_side_fork[k]) cudaEventDestroy(c->ev_side_fork[k]);
+        if (c->ev_side_join[k]) cudaEventDestroy(c->ev_side_join[k]);
+    }
     for (int i = 0; i <= CSV_NTYPES; i++) c->d_goff[i].release();
     for (int t = 0; t < CSV_NTYPES; t++) {
         c->sig[t].chrom.release(); c->sig[t].a.release(); c->sig[t].b.release(); c->sig[t].rid.release(); c->sig[t].c.release();
@@ -777,9 +800,19 @@ static int run_segment_and_cluster(csv_ctx* c, TypeJob& J, int t, uint32_t kslot
     if ((J.cp.min_support + 31) / 32 + 1 <= HEAD_MAX_NEED_WORDS) {
         MemberRec MR;
         memset(&MR, 0, sizeof(MR));
+        J.small_list = nullptr; J.n_small = nullptr; J.rest_list = nullptr; J.n_rest = nullptr;
         if ((t == CSV_DEL || t == CSV_INS) && J.iv.rec) {
             MR.rec = const_cast<IndelRec*>(J.iv.rec); MR.recc = const_cast<int32_t*>(J.iv.recc);
             MR.a = J.iv.a; MR.b = J.iv.b; MR.rid = J.iv.rid; MR.c = J.iv.recc ? J.iv.c : nullptr; MR.sidx = J.iv.sidx;
+            if (J.cp.keep >= 1.0 && J.small_path) {   // the walk also sorts the kept clusters into the two lists of the cluster kernels
+                CU(c->rest_list.ensure((size_t)c->kept_cap[t] * 12 + 64));
+                if (c->ticket_next + 2 >= (int)LB_ORDINALS) return set_err(CSV_E_STATE, "ticket pool exhausted");
+                MR.rest_list = c->rest_list.as<uint32_t>();
+                MR.small_list = (uint2*)(c->rest_list.as<uint32_t>() + c->kept_cap[t] + (c->kept_cap[t] & 1u));
+                MR.n_small = c->tickets.as<uint32_t>() + c->ticket_next++;
+                MR.n_rest = c->tickets.as<uint32_t>() + c->ticket_next++;
+                J.small_list = MR.small_list; J.n_small = MR.n_small; J.rest_list = MR.rest_list; J.n_rest = MR.n_rest;
+            }
         }
         LAUNCH(c, k_select_heads, grid_for(c, J.n_host, SEL_TILE, 4), SEL_THREADS, 0, J, c->kept[t].as<uint32_t>(), c->kept_cap[t],
                &ctr->n_kept[t], ts, &ctr->status, (uint32_t)ST_LIST_OVERFLOW, MR);
@@ -797,22 +830,29 @@ static int run_segment_and_cluster(csv_ctx* c, TypeJob& J, int t, uint32_t kslot
     if (c->ticket_next >= (int)LB_ORDINALS) return set_err(CSV_E_STATE, "ticket pool exhausted");
     uint32_t* work = c->tickets.as<uint32_t>() + c->ticket_next++;  // zeroed per call
     const bool keep_all = J.cp.keep >= 1.0;
-    J.rest_list = nullptr; J.n_rest = nullptr;
+    cudaStream_t side = nullptr;   // the general kernels' stream while the register kernel runs on the lane's own
     if (kind_of(t) == 0 && keep_all && J.small_path) {
-        // clusters of <= 32 members: register kernel; it lists the others for the general kernel
-        CU(c->rest_list.ensure((size_t)c->kept_cap[t] * 4 + 64));
         if (c->ticket_next + 2 >= (int)LB_ORDINALS) return set_err(CSV_E_STATE, "ticket pool exhausted");
         uint32_t* work_s = c->tickets.as<uint32_t>() + c->ticket_next++;
-        uint32_t* n_rest = c->tickets.as<uint32_t>() + c->ticket_next++;
         TypeJob JS = J;
-        JS.rest_list = c->rest_list.as<uint32_t>();
-        // (the small kernel counts the listed clusters in ctr->pad[1] of... a ticket word: see below)
-        JS.n_rest = n_rest;
+        uint32_t* n_rest = nullptr;
+        if (!J.small_list) {   // gather mode: the register kernel sizes the clusters itself and lists the larger ones
+            CU(c->rest_list.ensure((size_t)c->kept_cap[t] * 12 + 64));
+            n_rest = c->tickets.as<uint32_t>() + c->ticket_next++;
+            JS.rest_list = c->rest_list.as<uint32_t>();
+            JS.n_rest = n_rest;
+        } else if (!c->profiling) {
+            // both lists exist already: fork, the general kernels run beside the register kernel
+            side = c->side_stream[t == CSV_INS ? 1 : 0];
+            CU(cudaEventRecord(c->ev_side_fork[t == CSV_INS ? 1 : 0], c->stream));
+            CU(cudaStreamWaitEvent(side, c->ev_side_fork[t == CSV_INS ? 1 : 0], 0));
+        }
         if (t == CSV_INS) LAUNCH_NAMED(c, "k_cluster_small<INS>", (k_cluster_small<true>), c->n_sm * 6, 256, 0, JS, E, ctr, work_s, n_rest);
         else LAUNCH_NAMED(c, "k_cluster_small<DEL>", (k_cluster_small<false>), c->n_sm * 6, 256, 0, JS, E, ctr, work_s, n_rest);
-        J.rest_list = c->rest_list.as<uint32_t>();
-        J.n_rest = n_rest;
-    }
+        if (!J.small_list) { J.rest_list = JS.rest_list; J.n_rest = n_rest; }
+    } else { J.small_list = nullptr; J.n_small = nullptr; J.rest_list = nullptr; J.n_rest = nullptr; }
+    cudaStream_t lane_stream = c->stream;
+    if (side) c->stream = side;
     switch (kind_of(t)) {   // one per-type routine per kernel instantiation (instruction-cache footprint)
         case 0:
             if (t == CSV_DEL) { if (keep_all) launch_cluster_kind<6, 0>(c, J, E, ctr, work, smem_warp); else launch_cluster_kind<4, 0>(c, J, E, ctr, work, smem_warp); }
@@ -821,6 +861,11 @@ static int run_segment_and_cluster(csv_ctx* c, TypeJob& J, int t, uint32_t kslot
         case 1: launch_cluster_kind<1, 1>(c, J, E, ctr, work, smem_warp); break;
         case 2: launch_cluster_kind<2, 2>(c, J, E, ctr, work, smem_warp); break;
         default: launch_cluster_kind<3, 3>(c, J, E, ctr, work, smem_warp); break;
+    }
+    if (side) {
+        c->stream = lane_stream;
+        CU(cudaEventRecord(c->ev_side_join[t == CSV_INS ? 1 : 0], side));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_side_join[t == CSV_INS ? 1 : 0], 0));
     }
     stage_end(c, CSV_ST_CLUSTER);
     return CSV_OK;

@@ -46,7 +46,9 @@ static int nccl_load() {
         if (r__ != ncclSuccess) return set_err(CSV_E_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r__));    \
     } while (0)
 
+static void p2p_release(csv_ctx* c);
 static void comm_destroy(csv_ctx* c) {
+    p2p_release(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     c->comm = nullptr;
 }
@@ -73,6 +75,7 @@ extern "C" int csv_comm_init(csv_ctx* c, const void* id, int rank, int world) {
     NC(g_nccl.CommInitRank(&c->comm, world, u, rank));
     c->rank = rank; c->world = world;
     c->pad_cand = c->pad_names = 0;
+    c->p2p.failed = false; c->p2p.epoch = 0;
     if (!c->h_gather) CU(cudaMallocHost((void**)&c->h_gather, 4 * sizeof(int64_t) * 1024));
     return CSV_OK;
 }
@@ -144,6 +147,8 @@ struct MergeJob {
     const char* recv; GatherLayout L; int world; int32_t n_contigs;
     csv_cand* out_c; csv_geno* out_g; int32_t* out_n; int64_t cap_c, cap_n;
     int64_t* hdr;   // [world * GH_WORDS + 1]: compact copy of the headers + a status word (one D2H copy)
+    const unsigned long long* flags;   // peer-to-peer path: flags[r] == epoch once rank r's message has landed (null: NCCL path)
+    unsigned long long epoch;
 };
 __device__ __forceinline__ const int64_t* gm_header(const MergeJob& M, int r) { return (const int64_t*)(M.recv + (int64_t)r * M.L.msg_bytes); }
 __device__ __forceinline__ int64_t gm_valid(const MergeJob& M, int r) {
@@ -167,6 +172,20 @@ __global__ void __launch_bounds__(256) k_gather_merge(MergeJob M) {
     extern __shared__ uint32_t s_gm[];   // table path: [n_keys] exclusive offset of every key group, then [world * n_keys] of every (rank, key)
     __shared__ uint32_t s_warp[9];
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if (M.flags) {
+        // peer-to-peer gather: every rank stored its message into this rank's mail box over NVLink and then released its flag;
+        // wait (system-scope acquire) until all of them have landed.  A peer that never arrives ends the wait after ~1 s
+        // with an error status instead of hanging the GPU.
+        if ((int)threadIdx.x < M.world) {
+            const long long t0 = clock64();
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(M.flags + threadIdx.x) : "memory");
+                if (v != M.epoch && clock64() - t0 > 2000000000ll) { M.hdr[M.world * GH_WORDS] = 3; break; }
+            } while (v != M.epoch);
+        }
+        __syncthreads();
+    }
     if (tid < (int64_t)M.world * GH_WORDS) M.hdr[tid] = gm_header(M, (int)(tid / GH_WORDS))[tid % GH_WORDS];
     const int64_t per = M.L.pad_cand, total = per * M.world;
     const int T = M.L.n_keys;
@@ -247,6 +266,113 @@ __global__ void __launch_bounds__(256) k_gather_merge(MergeJob M) {
     }
 }
 
+// ---- peer-to-peer all-gather: no NCCL call in the step -------------------------------------------------------------------
+// Every rank owns a mail box (2 buffers x world slots + arrival flags) that all peers map through CUDA IPC.  A step's gather is
+// one kernel that stores the packed message into slot [rank] of every peer's box over NVLink / NVSwitch and, when the last
+// CTA has finished (system-scope fence), releases flag [rank] = epoch in every box; the merge kernel of each rank waits for
+// the world's flags.  Two buffers alternate by step: a rank can only be one step ahead of a peer (its merge of step k
+// waited for that peer's flag of step k), so a slot is never overwritten while its owner still reads it.
+struct PushJob {
+    const char* msg; int64_t msg_bytes; int world;
+    char* const* slots;                  // [world] this rank's slot in every peer's current buffer
+    unsigned long long* const* flags;    // [world] this rank's flag in every peer's current buffer
+    unsigned long long epoch;
+    uint32_t* done;
+};
+__global__ void __launch_bounds__(256) k_gather_push(PushJob J) {
+    __shared__ uint32_t s_last;
+    const int64_t n16 = J.msg_bytes / 16;
+    const uint4* src = (const uint4*)J.msg;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < n16; i += stride) {
+        const uint4 v = src[i];
+        for (int p = 0; p < J.world; p++) ((uint4*)J.slots[p])[i] = v;
+    }
+    __threadfence_system();
+    if (threadIdx.x == 0) s_last = atomicAdd(J.done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if ((int)threadIdx.x < J.world) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(J.flags[threadIdx.x]), "l"(J.epoch) : "memory");
+    }
+    if (threadIdx.x == 0) *J.done = 0u;   // ready for the next step (stream order)
+}
+
+static void p2p_release(csv_ctx* c) {
+    csv_ctx::P2PState& X = c->p2p;
+    for (size_t r = 0; r < X.peer.size(); r++)
+        if (X.peer[r] && (int)r != c->rank) cudaIpcCloseMemHandle(X.peer[r]);
+    X.peer.clear();
+    if (X.box) cudaFree(X.box);
+    X.box = nullptr;
+    X.d_tab.release();
+    X.ready = false;
+}
+
+// (re)build the mail boxes for messages of msg_bytes: collective (handles travel through one ncclAllGather)
+static int p2p_setup(csv_ctx* c, int64_t msg_bytes) {
+    csv_ctx::P2PState& X = c->p2p;
+    const int W = c->world;
+    CU(cudaStreamSynchronize(c->stream));
+    p2p_release(c);
+    X.slot_bytes = msg_bytes;
+    X.flags_off = (size_t)2 * W * msg_bytes;
+    const size_t total = X.flags_off + (size_t)2 * W * 8 + 256;
+    cudaError_t e = cudaMalloc(&X.box, total);
+    if (e != cudaSuccess) return set_err(CSV_E_CUDA, "cudaMalloc(mail box): %s", cudaGetErrorString(e));
+    CU(cudaMemset(X.box, 0, total));
+    CU(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t mine;
+    e = cudaIpcGetMemHandle(&mine, X.box);
+    // a rank that cannot export still takes part in the exchange (all-zero handle): every rank then falls back to NCCL together
+    int ok = e == cudaSuccess ? 1 : 0;
+    if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(c->g_scratch.ensure((size_t)(W + 1) * 80 + (size_t)(W * GH_WORDS + 8) * 8, true));
+    char* d_send = c->g_scratch.as<char>() + (size_t)(W * GH_WORDS + 8) * 8;
+    char* d_recv = d_send + 80;
+    char hbuf[80];
+    memset(hbuf, 0, sizeof(hbuf));
+    memcpy(hbuf, &mine, 64);
+    hbuf[64] = (char)ok;
+    CU(cudaMemcpyAsync(d_send, hbuf, 80, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather(d_send, d_recv, 80, ncclUint8, c->comm, c->stream));
+    std::vector<char> all((size_t)W * 80);
+    CU(cudaMemcpyAsync(all.data(), d_recv, (size_t)W * 80, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < W; r++) ok &= all[(size_t)r * 80 + 64] ? 1 : 0;
+    X.peer.assign(W, nullptr);
+    if (ok) {
+        for (int r = 0; r < W && ok; r++) {
+            if (r == c->rank) { X.peer[r] = X.box; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all.data() + (size_t)r * 80, 64);
+            e = cudaIpcOpenMemHandle(&X.peer[r], h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { cudaGetLastError(); X.peer[r] = nullptr; ok = 0; }
+        }
+    }
+    // every rank must take the same path: agree on "all ranks mapped all boxes"
+    int64_t flag = ok;
+    CU(cudaMemcpyAsync(d_send, &flag, 8, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllReduce(d_send, d_send, 1, ncclInt64, ncclMin, c->comm, c->stream));
+    CU(cudaMemcpyAsync(&flag, d_send, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (!flag) { p2p_release(c); X.failed = true; return CSV_OK; }   // NCCL path from now on
+    // device tables: [buf][peer] slot pointer of this rank, then [buf][peer] flag pointer
+    std::vector<void*> tab((size_t)4 * W);
+    for (int b = 0; b < 2; b++)
+        for (int r = 0; r < W; r++) {
+            tab[(size_t)b * W + r] = (char*)X.peer[r] + ((size_t)b * W + c->rank) * msg_bytes;
+            tab[(size_t)(2 + b) * W + r] = (char*)X.peer[r] + X.flags_off + ((size_t)b * W + c->rank) * 8;
+        }
+    CU(X.d_tab.ensure(tab.size() * sizeof(void*) + 64, true));
+    CU(cudaMemcpy(X.d_tab.p, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice));
+    CU(cudaMemset((char*)X.d_tab.p + tab.size() * sizeof(void*), 0, 64));   // the push kernel's done counter
+    X.ready = true;
+    return CSV_OK;
+}
+
 static int gather_enqueue(csv_ctx* c) {
     const GatherLayout L = gather_layout(c->pad_cand, c->pad_names, c->n_contigs, c->world);
     const int W = c->world;
@@ -260,9 +386,33 @@ static int gather_enqueue(csv_ctx* c) {
     if (L.n_keys) CU(cudaMemsetAsync(c->g_send.as<char>() + L.off_tab, 0, (size_t)L.n_keys * 8, c->stream));
     LAUNCH(c, k_gather_pack, c->n_sm * 2, 256, 0, c->cand.as<csv_cand>(), c->geno.as<csv_geno>(), c->names.as<int32_t>(),
            c->counters.as<Counters>(), c->cap_cand, c->cap_names, L, c->rank, c->g_send.as<char>());
-    NC(g_nccl.AllGather(c->g_send.p, c->g_recv.p, (size_t)L.msg_bytes, ncclUint8, c->comm, c->stream));
+    csv_ctx::P2PState& X = c->p2p;
+    const bool want_p2p = c->p2p_enabled && !X.failed && W > 1;
+    if (want_p2p && (!X.ready || X.slot_bytes != L.msg_bytes)) {   // first gather / the padding changed: collective re-setup
+        int prc = p2p_setup(c, L.msg_bytes);
+        if (prc) return prc;
+    }
     MergeJob M;
-    M.recv = c->g_recv.as<char>(); M.L = L; M.world = W; M.n_contigs = c->n_contigs;
+    if (want_p2p && X.ready) {
+        // pack -> push into every peer's mail box -> merge (which waits for the world's flags): no NCCL call in the step
+        X.epoch++;
+        const int b = (int)(X.epoch & 1ull);
+        PushJob J;
+        J.msg = c->g_send.as<char>(); J.msg_bytes = L.msg_bytes; J.world = W;
+        J.slots = (char* const*)((void**)X.d_tab.p + (size_t)b * W);
+        J.flags = (unsigned long long* const*)((void**)X.d_tab.p + (size_t)(2 + b) * W);
+        J.epoch = X.epoch;
+        J.done = (uint32_t*)((void**)X.d_tab.p + (size_t)4 * W);
+        LAUNCH(c, k_gather_push, std::min(c->n_sm, (int)std::max<int64_t>(L.msg_bytes / 16 / 256, 1)), 256, 0, J);
+        M.recv = (const char*)X.box + (size_t)b * W * L.msg_bytes;
+        M.flags = (const unsigned long long*)((const char*)X.box + X.flags_off) + (size_t)b * W;
+        M.epoch = X.epoch;
+    } else {
+        NC(g_nccl.AllGather(c->g_send.p, c->g_recv.p, (size_t)L.msg_bytes, ncclUint8, c->comm, c->stream));
+        M.recv = c->g_recv.as<char>();
+        M.flags = nullptr; M.epoch = 0;
+    }
+    M.L = L; M.world = W; M.n_contigs = c->n_contigs;
     M.out_c = c->g_cand.as<csv_cand>(); M.out_g = c->g_geno.as<csv_geno>(); M.out_n = c->g_names.as<int32_t>();
     M.cap_c = L.pad_cand * W; M.cap_n = L.pad_names * W;
     M.hdr = c->g_scratch.as<int64_t>();
@@ -321,6 +471,10 @@ extern "C" int csv_gathered_counts(csv_ctx* c, int64_t* n_cand, int64_t* n_names
             mc = std::max(mc, h[0]); mn = std::max(mn, h[1]);
         }
         if (!over) {
+            if (c->h_gather[4 * c->world] == 3) {
+                cudaMemsetAsync(c->g_scratch.as<int64_t>() + 4 * c->world, 0, 8, c->stream);
+                return set_err(CSV_E_CUDA, "csv_allgather: a peer's message did not arrive (peer-to-peer gather timed out)");
+            }
             if (c->h_gather[4 * c->world] != 0) {
                 cudaMemsetAsync(c->g_scratch.as<int64_t>() + 4 * c->world, 0, 8, c->stream);
                 return set_err(CSV_E_CUDA, "csv_allgather: merge failed (status %lld)", (long long)c->h_gather[4 * c->world]);

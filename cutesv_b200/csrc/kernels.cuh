@@ -41,6 +41,8 @@ struct TypeJob {
     int small_path;          // INS / DEL: clusters of <= 32 members go through the register kernel (k_cluster_small) first
     uint32_t* rest_list;     // ... which lists the others here (kept-cluster ordinals); null: the general kernel takes every cluster
     const uint32_t* n_rest;
+    uint2* small_list;       // (ordinal, members) of the clusters of <= 32 members, written by k_select_heads in record mode
+    const uint32_t* n_small;
 };
 
 __device__ __forceinline__ int64_t job_n(const TypeJob& J) { return J.n_dev ? (int64_t)*J.n_dev : J.n_host; }
@@ -90,6 +92,9 @@ struct MemberRec {
     IndelRec* rec; int32_t* recc;
     const int32_t *a, *b, *rid, *c;
     const uint32_t* sidx;
+    // classification of the kept clusters by size while their records are gathered (null: not wanted)
+    uint2* small_list; uint32_t* n_small;    // (kept ordinal, members) for <= 32 members
+    uint32_t* rest_list; uint32_t* n_rest;   // kept ordinal for the others
 };
 __global__ void __launch_bounds__(SEL_THREADS) k_select_heads(TypeJob J, uint32_t* out, uint32_t out_cap, uint32_t* out_count,
                                                               TileSync ts, uint32_t* status_word, uint32_t overflow_bit, MemberRec MR) {
@@ -190,8 +195,12 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_heads(TypeJob J, uint32_
                         *reinterpret_cast<int4*>(&MR.rec[i]) = *reinterpret_cast<const int4*>(&r);
                         if (MR.recc) MR.recc[i] = c5;
                     }
-                    if (bm) break;
+                    if (bm) { done += take; break; }
                     done += 32;
+                }
+                if (MR.small_list && lane == 0) {   // `done` = members of the cluster; its kept ordinal = s_excl + h
+                    if (done <= 32) MR.small_list[atomicAdd(MR.n_small, 1u)] = make_uint2(s_excl + h, (uint32_t)done);
+                    else MR.rest_list[atomicAdd(MR.n_rest, 1u)] = s_excl + h;
                 }
                 if (lane == 0) {   // the head itself
                     const uint32_t x = MR.sidx[s0];
@@ -951,28 +960,33 @@ __device__ __forceinline__ void indel_cluster_small(const IndelView& in, int64_t
     if (lane == 0) E.cnt[kslot] = n_emit;
 }
 
-// one warp per kept cluster of <= 32 members; larger ones are listed (rest_list) for the general kernel
+// one warp per kept cluster of <= 32 members.  Two ways in: (a) k_select_heads already sorted the kept clusters into
+// `small_list` (ordinal, members) and `rest_list` while it gathered their records, so this kernel and the general kernel run
+// side by side on two streams; (b) no lists (gather mode): every kept cluster is sized here and the larger ones are listed
+// for the general kernel, which then runs after this one.
 template <bool IS_INS>
 __global__ void __launch_bounds__(256) k_cluster_small(TypeJob J, Emit E, Counters* ctr, uint32_t* work, uint32_t* n_rest) {
     const int lane = threadIdx.x & 31;
     const int64_t n = job_n(J);
-    const uint32_t n_kept = ctr->n_kept[J.svtype];
+    const uint32_t n_todo = J.small_list ? *J.n_small : ctr->n_kept[J.svtype];
     uint32_t k_next = 0, n_done = 0, n_mem = 0;
     if (lane == 0) k_next = atomicAdd(work, 1u);
     while (true) {
-        const uint32_t k = __shfl_sync(0xffffffffu, k_next, 0);
-        if (k >= n_kept) break;
+        const uint32_t q = __shfl_sync(0xffffffffu, k_next, 0);
+        if (q >= n_todo) break;
         if (lane == 0) k_next = atomicAdd(work, 1u);
-        const int64_t s = J.kept_start[k];
-        const int m = cluster_size_warp(J, s, n, 32);
-        if (m > 32) {
-            if (lane == 0) {
-                const uint32_t o = atomicAdd(n_rest, 1u);
-                J.rest_list[o] = k;   // (capacity = kept capacity of the type)
+        uint32_t k;
+        int m;
+        if (J.small_list) { const uint2 e = J.small_list[q]; k = e.x; m = (int)e.y; }
+        else {
+            k = q;
+            m = cluster_size_warp(J, J.kept_start[k], n, 32);
+            if (m > 32) {
+                if (lane == 0) J.rest_list[atomicAdd(n_rest, 1u)] = k;   // (capacity = kept capacity of the type)
+                continue;
             }
-            continue;
         }
-        indel_cluster_small<IS_INS>(J.iv, s, m, J.cp, J.kslot_base + k, E);
+        indel_cluster_small<IS_INS>(J.iv, J.kept_start[k], m, J.cp, J.kslot_base + k, E);
         n_done++; n_mem += (uint32_t)m;
     }
     if (lane == 0) {
