@@ -8,8 +8,9 @@ A "step" = one pass of the hot path (density filter -> sort -> chain-linkage clu
 over one batch of synthetic signature arrays.  N = 1: BASELINE.json configs[1] "synthetic 30x ONT whole-genome
 signature arrays, resolution_INS + resolution_DEL on 1xB200" (16 777 216 signatures, 7.75 M reads-table rows,
 --genotype).  N > 1: BASELINE.json configs[3]: the SAME genome contig-sharded (LPT) over the N GPUs -- one process
-per GPU, csv_set_shard, no data-path collective -- and the step ENDS with csv_allgather (ONE ncclAllGather of the
-final records + the device merge into the single-GPU order), inside the timed region ("scaling": "strong").
+per GPU, csv_set_shard, no data-path collective -- and the step ENDS with csv_allgather (ONE gather of the final
+records -- stores into the peers' mail boxes over NVLink, or ONE ncclAllGather with CUTESV_B200_GATHER=nccl -- + the
+device merge into the single-GPU order), inside the timed region ("scaling": "strong").
 --weak keeps one genome-equivalent per GPU instead.
 
   value  device-resident throughput (inputs already in HBM), CUDA events on the launching stream, max over ranks
@@ -334,7 +335,7 @@ def main():
     eng.set_profiling(False)
     eng.set_lanes(True)
     # all-gather alone (N > 1): warmed, between its own events, after a barrier
-    allgather_ms = 0.0
+    allgather_ms, allgather_other_ms, gather_mode, other_mode = 0.0, 0.0, None, None
     if world > 1:
         for _ in range(3):
             eng.allgather()
@@ -347,6 +348,21 @@ def main():
         barrier()
         allgather_ms = a0.elapsed_time(a1) / 10.0
         eng.gathered_counts()
+        gather_mode = eng.gather_mode()
+        # A/B: the other gather (ncclAllGather <-> peer-to-peer stores), same protocol
+        eng.set_gather(gather_mode == "nccl")
+        for _ in range(3):
+            eng.allgather()
+        barrier()
+        a0.record(stream)
+        for _ in range(10):
+            eng.allgather()
+        a1.record(stream)
+        barrier()
+        allgather_other_ms = a0.elapsed_time(a1) / 10.0
+        other_mode = eng.gather_mode()
+        eng.gathered_counts()
+        eng.set_gather(gather_mode != "nccl")
 
     # ---------------- end to end through the public call: e2e ----------------
     cap_c = max(2 * max(n_cand, gathered[0]) + 1024, 1024)
@@ -404,7 +420,7 @@ def main():
             # per-launch quantities: INS/DEL kernels run once per type
             indel = [k for k in ("DEL", "INS") if k in cfg["sigs"]]
             q = dict(n=np.mean([len(cfg["sigs"][k]["chrom"]) for k in indel]) if indel else 0.0,
-                     S=np.mean([ctrs["domain"][k] for k in indel]) if indel else 0.0,
+                     S=np.mean([(ctrs["domain"][k] or len(cfg["sigs"][k]["chrom"])) for k in indel]) if indel else 0.0,   # no density filter: every signature is sorted
                      M=np.mean([ctrs["members"][k] for k in indel]) if indel else 0.0,
                      R=float(len(cfg["reads"]["chrom"])), C=float(n_cand) / n_types, P=float(ctrs["pairs"]), B=lin_total / 256.0)
             nbytes = kernel_bytes(nm, q)
@@ -439,7 +455,8 @@ def main():
                                        if world > 1 else "single GPU x%d") % world,
                        "l2": "inputs (%.0f MB/step on rank 0) larger than the 126 MB L2, no explicit flush" % (dev_in / 1e6),
                        "e2e_inputs": "host columns grouped by contig + row offsets (csv_upload_*_grouped), pinned",
-                       "allgather_ms_alone": allgather_ms, "allgather_in_step": world > 1,
+                       "allgather_ms_alone": allgather_ms, "allgather_in_step": world > 1, "allgather_mode": gather_mode,
+                       "allgather_ms_alone_other_mode": {other_mode: allgather_other_ms} if other_mode else None,
                        "density_filter_survivors": ctrs["domain"], "kept_clusters": ctrs["kept"],
                        "graph_replays_in_timed_region": int(replays)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -65,6 +65,8 @@ _SIGNATURES = {
     "csv_comm_init": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
     "csv_comm_destroy": (C.c_int, [_VP]),
     "csv_allgather": (C.c_int, [_VP]),
+    "csv_set_gather": (C.c_int, [_VP, C.c_int]),
+    "csv_gather_mode": (C.c_int, [_VP]),
     "csv_gathered_counts": (C.c_int, [_VP, _I64P, _I64P]),
     "csv_fetch_gathered": (C.c_int, [_VP, _VP, _VP, C.c_int64, _I32P, C.c_int64]),
     "csv_gathered_device_ptrs": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),

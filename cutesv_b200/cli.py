@@ -275,6 +275,10 @@ def main_ctrl(args, argv, engine=None):
                 results.setdefault(chrom, []).extend(r)
     logging.info("Writing to your output file.")
     reference = vcf.IndexedFasta(args.reference)   # random access through <ref>.fai (built on the fly when missing)
+    for name, n in contig_info:   # a stale .fai / another assembly would give wrong REF bases without any error
+        have = reference.length_of(name)
+        if have is not None and have != n:
+            logging.warning("contig %s: %d bp in the BAM header but %d bp in %s (stale .fai or another assembly?)" % (name, n, have, args.reference))
     opts = dict(genotype=args.genotype, max_size=args.max_size, min_size=args.min_size, report_readid=args.report_readid,
                 ignore_sequence=args.ignore_sequence)
     vcf.write_vcf(args.output, results, reference, contig_info, args.sample, argv, opts)

@@ -80,6 +80,13 @@ extern "C" int csv_comm_init(csv_ctx* c, const void* id, int rank, int world) {
     return CSV_OK;
 }
 
+extern "C" int csv_set_gather(csv_ctx* c, int peer_to_peer) {
+    if (!c) return set_err(CSV_E_INVALID, "null ctx");
+    c->p2p_enabled = peer_to_peer != 0;
+    return CSV_OK;
+}
+extern "C" int csv_gather_mode(csv_ctx* c) { return c && c->p2p_enabled && c->p2p.ready && !c->p2p.failed ? 1 : 0; }
+
 extern "C" int csv_comm_destroy(csv_ctx* c) {
     if (!c) return set_err(CSV_E_INVALID, "null ctx");
     comm_destroy(c);

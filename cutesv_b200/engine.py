@@ -218,6 +218,13 @@ class Engine(object):
         """Asynchronous, collective: pack + ONE ncclAllGather + device merge of the records of the last cluster_device()."""
         _lib.check(self.L.csv_allgather(self.h))
 
+    def set_gather(self, peer_to_peer):
+        """True: store into the peers' mail boxes over NVLink (CUDA IPC); False: ncclAllGather."""
+        _lib.check(self.L.csv_set_gather(self.h, 1 if peer_to_peer else 0))
+
+    def gather_mode(self):
+        return "peer-to-peer" if self.L.csv_gather_mode(self.h) else "nccl"
+
     def gathered_counts(self):
         nc, nn = C.c_int64(0), C.c_int64(0)
         _lib.check(self.L.csv_gathered_counts(self.h, C.byref(nc), C.byref(nn)))
@@ -301,6 +308,11 @@ def _extract_method(self, packed, append=False):
     return dict(counts={name: int(counts[t]) for t, name in enumerate(_abi.TYPE_NAMES)}, n_rows=int(n_rows.value),
                 first={name: first[t] for t, name in enumerate(_abi.TYPE_NAMES)}, first_rows=first_rows, first_pieces=first_pieces,
                 n_pieces=self._ex_pieces)
+
+
+def _extract_skipped_method(self):
+    """Records whose split-read analysis was skipped (more than 64 qualifying segments, only with max_split_parts -1)."""
+    return int(self.L.csv_extract_skipped(self.h))
 
 
 def _extract_reset_method(self):
@@ -389,6 +401,7 @@ def _fetch_extracted_method(self):
 
 Engine.pin_packet = _pin_packet_method
 Engine.extract_reset = _extract_reset_method
+Engine.extract_skipped = _extract_skipped_method
 Engine.fetch_ins_pieces = _fetch_ins_pieces_method
 Engine.fetch_sig_cols = _fetch_sig_cols_method
 Engine.remap_read_ids = _remap_read_ids_method

@@ -241,6 +241,12 @@ class IndexedFasta(object):
                 self.full = read_fasta(path)
         self.fh = open(path, "rb") if self.full is None else None
 
+    def length_of(self, name):
+        """Sequence length of a contig according to the index (None when the contig is absent)."""
+        if self.full is not None:
+            return len(self.full[name]) if name in self.full else None
+        return self.entries[name][0] if name in self.entries else None
+
     def _build(self, path):
         name, length, offset, lb, lw, short_seen, pos = None, 0, 0, 0, 0, False, 0
         with open(path, "rb") as f:

@@ -333,11 +333,16 @@ int csv_comm_unique_id(void* id, size_t bytes);
 int csv_comm_init(csv_ctx* ctx, const void* id, int rank, int world);
 int csv_comm_destroy(csv_ctx* ctx);
 /* After csv_cluster, asynchronous on the ctx stream, collective: packs this rank's records (csv_cand, csv_geno,
- * supporting read ids) into one padded message, ONE ncclAllGather over NVLink, then merges the messages of all
- * ranks on the device into the single-GPU order (svtype, contig id, emission order).  csv_cand.reserved[1] of a
+ * supporting read ids) into one padded message, gathers the messages of all ranks, then merges them on the device
+ * into the single-GPU order (svtype, contig id, emission order).  The gather itself is either ONE ncclAllGather over
+ * NVLink or (default when every rank could map every rank's mail box through CUDA IPC) ONE kernel that stores the
+ * message into the peers' mail boxes over NVLink and releases an arrival flag; csv_set_gather(ctx, 0) or
+ * CUTESV_B200_GATHER=nccl selects NCCL, csv_gather_mode() tells which one the last gather used (1 peer-to-peer).  csv_cand.reserved[1] of a
  * gathered record is its source rank (csv_cand.aux of an INS row indexes THAT rank's INS signatures).  The padded
  * message size is agreed once (first call: one count all-reduce) and re-agreed only when a rank outgrows it. */
 int csv_allgather(csv_ctx* ctx);
+int csv_set_gather(csv_ctx* ctx, int peer_to_peer);
+int csv_gather_mode(csv_ctx* ctx);
 /* Blocks until the gather finished; total sizes over all ranks. */
 int csv_gathered_counts(csv_ctx* ctx, int64_t* n_cand, int64_t* n_names);
 int csv_fetch_gathered(csv_ctx* ctx, csv_cand* cands, csv_geno* genos, int64_t cap_cand, int32_t* names, int64_t cap_names);

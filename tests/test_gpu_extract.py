@@ -169,3 +169,41 @@ def test_remap_read_ids_and_swap_rows(engine):
     for k in ("chrom", "a", "b", "read_id", "c"):
         assert np.array_equal(sw["sigs"]["INS"][k], after["sigs"]["INS"][k][perm]), k
     assert np.array_equal(sw["piece_off"], after["piece_off"][perm]) and np.array_equal(sw["piece_cnt"], after["piece_cnt"][perm])
+
+
+def _many_segment_packet():
+    """Three records; the middle one carries 70 SA segments (more than the 64 the split-read engine holds)."""
+    reads, names, lens = synth.synth_alignments(21, 3)
+    for r in reads:
+        r.flag, r.mapq = 0, 60
+    r = reads[1]
+    L = r.query_length
+    ents = []
+    for j in range(70):
+        a = (j * L) // 71
+        b = ((j + 1) * L) // 71
+        ents.append("%s,%d,+,%dS%dM%dS,60,1" % (r.reference_name, r.reference_end + 50 * j + 1, a, max(b - a, 1), max(L - b, 0)))
+    r.tags = [("NM", 1), ("SA", ";".join(ents) + ";")]
+    rnames = sorted(set(x.query_name for x in reads))
+    pk = packing.pack_alignments(reads, {nm: i for i, nm in enumerate(names)}, {nm: i for i, nm in enumerate(rnames)})
+    return reads, names, lens, rnames, pk
+
+
+def test_more_than_64_segments_is_counted_not_fatal(engine):
+    """--max_split_parts -1 with a record of 70 segments: round 1 failed the whole call (CSV_E_INPUT); now the record's split-read
+    analysis is skipped and counted, everything else (its CIGAR signatures, the other records) is extracted as usual."""
+    reads, names, lens, rnames, pk = _many_segment_packet()
+    p = _abi.default_params(max_split_parts=-1, min_mapq=0, min_read_len=100)
+    engine.set_params(p)
+    engine.set_contigs(lens)
+    engine.extract(pk)
+    got = engine.fetch_extracted()
+    assert engine.extract_skipped() == 1
+    ref = emul_lib.extract(p, pk)
+    assert _canon(got) == _canon(ref)
+    # the same packet without the long record gives the same split signatures: only that record's were skipped
+    p7 = _abi.default_params(max_split_parts=7, min_mapq=0, min_read_len=100)   # the reference's default drops the record's split analysis too
+    engine.set_params(p7)
+    engine.extract(pk)
+    assert engine.extract_skipped() == 0
+    assert _canon(engine.fetch_extracted())["DEL"] == _canon(got)["DEL"]

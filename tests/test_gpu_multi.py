@@ -1,4 +1,5 @@
-"""-m gpu, needs >= 2 devices: merged N-rank result (contig shards + csv_allgather) == oracle on the whole genome."""
+"""-m gpu, needs >= 2 devices: merged N-rank result (contig shards + csv_allgather) == oracle on the whole genome, through both
+gathers (peer-to-peer mail boxes over CUDA IPC = default, ncclAllGather) and through a forced re-negotiation of the padded size."""
 import os
 import socket
 import subprocess
@@ -23,7 +24,8 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("cid,scale,env", [(2, 0.05, {}), (3, 0.05, {}), (2, 0.02, {"CUTESV_B200_GATHER_PAD": "8"})])
+@pytest.mark.parametrize("cid,scale,env", [(2, 0.05, {}), (3, 0.05, {}), (2, 0.02, {"CUTESV_B200_GATHER_PAD": "8"}),
+                                            (2, 0.05, {"CUTESV_B200_GATHER": "nccl"}), (3, 0.05, {"CUTESV_B200_GATHER": "nccl", "CUTESV_B200_GATHER_PAD": "8"})])
 def test_sharded_ranks_match_oracle(cid, scale, env):
     n = _n_devices()
     if n < 2:
