@@ -130,6 +130,8 @@ class _Accumulator(object):
         self.aln = {k: [] for k in ("chrom", "start", "end", "read_id", "is_primary")}  # every record, BAM order
         self.aln_chunks = []
         self.merge = (min_siglength, merge_ins_threshold)
+        self.t_extract = 0.0    # seconds inside csv_extract_append (H2D of the packet + kernel (a) + counts)
+        self.t_ins_seq = 0.0    # seconds rebuilding INS sequence strings on the host
         eng.extract_reset()
 
     def rid(self, name):
@@ -143,7 +145,10 @@ class _Accumulator(object):
     def extract(self, packet, n_records, query_of, want_seq, cigar_of=None):
         """One packet through csv_extract_append.  query_of(rec) -> query sequence of packet record `rec`;
         cigar_of(rec) -> (uint32 CIGAR array, reference_start) for the rare signatures the host rebuilds."""
+        t0 = time.perf_counter()
         r = self.eng.extract(packet, append=True)
+        t1 = time.perf_counter()
+        self.t_extract += t1 - t0
         n_new = r["counts"]["INS"] - r["first"]["INS"]
         if want_seq and n_new:
             po, pc, pieces = self.eng.fetch_ins_pieces(r["first"]["INS"], n_new, r["first_pieces"], r["n_pieces"] - r["first_pieces"])
@@ -154,6 +159,7 @@ class _Accumulator(object):
         else:
             self.ins_seq.extend([""] * n_new)
         self.rec_base += n_records
+        self.t_ins_seq += time.perf_counter() - t1
 
     def add_alignment(self, chrom_id, read):
         a = self.aln
@@ -259,15 +265,28 @@ def main_ctrl(args, argv, engine=None):
     eng.set_contigs(np.array([lens[n] for n in chrom_names], dtype=np.int64))
     acc = _Accumulator(eng, args.min_siglength, args.merge_ins_threshold)
     want_seq = not args.ignore_sequence
+    stages = {}
+    t_stage = time.perf_counter()
+
+    def lap(name):
+        nonlocal t_stage
+        now = time.perf_counter()
+        stages[name] = stages.get(name, 0.0) + now - t_stage
+        t_stage = now
+
     names_rank = source.scan(args, eng, acc, tasks, bed, chrom_id, want_seq)
+    lap("scan")   # decode + pack + csv_extract_append per packet
     logging.info("Rebuilding signatures of structural variants.")
     read_names = acc.finish(*names_rank, want_seq=want_seq)   # the signatures never left the device
+    lap("names_and_ties")
     logging.info("Clustering structural variants.")
     eng.upload_alignments(acc.alignments(acc.rank) if args.genotype else None)
     eng.cluster_device(0x1F)
     cands, genos, names = eng.fetch()
     eng.upload_alignments(None)
+    lap("cluster_and_fetch")
     got = rows.records_to_rows(cands, genos, names, chrom_names, lambda k: read_names[k], lambda k: acc.ins_seq[k], bool(args.genotype))
+    lap("rows")
     results = {}
     for t in ("DEL", "INS", "INV", "DUP", "TRA"):  # submission order of the reference, cuteSV:1116-1199
         for (tt, chrom), r in got.items():
@@ -282,6 +301,13 @@ def main_ctrl(args, argv, engine=None):
     opts = dict(genotype=args.genotype, max_size=args.max_size, min_size=args.min_size, report_readid=args.report_readid,
                 ignore_sequence=args.ignore_sequence)
     vcf.write_vcf(args.output, results, reference, contig_info, args.sample, argv, opts)
+    lap("vcf")
+    # stage split of the wall time (scan = BAM decode + packing + the device extraction, of which csv_extract_append and the
+    # host rebuild of INS sequence strings are also given on their own)
+    stages["scan.csv_extract_append"] = acc.t_extract
+    stages["scan.ins_sequences"] = acc.t_ins_seq
+    main_ctrl.last_stages = dict(stages)
+    logging.info("Stage split (s): " + ", ".join("%s %.3f" % kv for kv in stages.items()))
     if args.retain_work_dir:   # the reference's pickle layout needs the signatures on the host: one D2H of the columns
         sigs = {t: eng.fetch_sig_cols(t) for t in _abi.TYPE_NAMES}
         _write_workdir(tmp, sigs, eng.fetch_read_rows(), chrom_names, read_names, acc.ins_seq, args.write_old_sigs)

@@ -226,7 +226,9 @@ struct csv_ctx {
     bool p2p_enabled = true;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
-    DBuf g_send, g_recv, g_cand, g_geno, g_names, g_scratch;
+    DBuf g_send, g_recv, g_cand, g_geno, g_names, g_scratch, g_tab;
+    bool pdl_enabled = true;            // programmatic dependent launches along the kernel chain (CUTESV_B200_PDL=0: off)
+    bool prev_is_chain_kernel = false;  // the launch being enqueued directly follows a chain kernel on the same stream
     DBuf cal_in0, cal_in1, cal_out, aln_flag;   // csv_cal_gl / csv_upload_alignments scratch (no per-call cudaMalloc)
     int64_t pad_cand = 0, pad_names = 0;
     int64_t* h_gather = nullptr;    // pinned: per-rank headers after the gather
@@ -245,6 +247,25 @@ static void kprof_end(csv_ctx* c);
         (ctx)->launches++;                                                             \
     } while (0)
 #define LAUNCH(ctx, kernel, grid, block, smem, ...) LAUNCH_NAMED(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
+// A kernel that directly follows another kernel of the chain on the same stream (no copy, memset or join in between) and that
+// begins with pdl_wait(): launched as a programmatic dependent, so its launch latency and its CTAs' start-up overlap the tail
+// of its predecessor.  Captured into the CUDA graph as a programmatic edge.  Off when profiling (events sit between launches).
+#define LAUNCH_PDL_NAMED(ctx, name, kernel, grid, block, smem, ...)                                          \
+    do {                                                                                                      \
+        if ((ctx)->pdl_enabled && !(ctx)->profiling) {                                                        \
+            cudaLaunchConfig_t cfg_;                                                                          \
+            memset(&cfg_, 0, sizeof(cfg_));                                                                   \
+            cfg_.gridDim = dim3((unsigned)(grid)); cfg_.blockDim = dim3((unsigned)(block));                   \
+            cfg_.dynamicSmemBytes = (smem); cfg_.stream = (ctx)->stream;                                      \
+            cudaLaunchAttribute at_[1];                                                                       \
+            at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                   \
+            at_[0].val.programmaticStreamSerializationAllowed = 1;                                            \
+            cfg_.attrs = at_; cfg_.numAttrs = 1;                                                              \
+            cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                                   \
+            (ctx)->launches++;                                                                                \
+        } else LAUNCH_NAMED(ctx, name, kernel, grid, block, smem, __VA_ARGS__);                               \
+    } while (0)
+#define LAUNCH_PDL(ctx, kernel, grid, block, smem, ...) LAUNCH_PDL_NAMED(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
 
 // KIND: the per-type routine of the warp kernel (0 INS/DEL generic, 1 DUP, 2 INV, 3 TRA, 4-7 INS/DEL specialisations, see
 // run_cluster); the CTA kernel (rare big clusters) always uses the generic routine BKIND in 0..3
@@ -254,7 +275,7 @@ static void launch_cluster_kind(csv_ctx* c, const TypeJob& J, const Emit& E, Cou
                                         "k_cluster_warp<DEL>", "k_cluster_warp<INS>", "k_cluster_warp<DEL,keep-all>", "k_cluster_warp<INS,keep-all>"};
     static const char* const nm_b[4] = {"k_cluster_block<INDEL>", "k_cluster_block<DUP>", "k_cluster_block<INV>", "k_cluster_block<TRA>"};
     LAUNCH_NAMED(c, nm_w[KIND], (k_cluster_warp<KIND>), c->n_sm * 3, CL_THREADS, smem_warp, J, E, ctr, work);
-    LAUNCH_NAMED(c, nm_b[BKIND], (k_cluster_block<BKIND>), c->n_sm, CL_THREADS, (size_t)BLOCK_M * ARENA_PER_MAX, J, E, ctr);
+    LAUNCH_PDL_NAMED(c, nm_b[BKIND], (k_cluster_block<BKIND>), c->n_sm, CL_THREADS, (size_t)BLOCK_M * ARENA_PER_MAX, J, E, ctr);
 }
 
 static int grid_for(const csv_ctx* c, int64_t n, int block, int per_sm = 8) {
@@ -404,6 +425,7 @@ extern "C" int csv_create(int device, void* stream, csv_ctx** out) {
     if (const char* e = getenv("CUTESV_B200_NO_PREFILTER")) c->prefilter_enabled = atoi(e) == 0;
     if (const char* e = getenv("CUTESV_B200_LANES")) c->lanes_enabled = atoi(e) != 0;
     if (const char* e = getenv("CUTESV_B200_GRAPHS")) c->graphs_enabled = atoi(e) != 0;
+    if (const char* e = getenv("CUTESV_B200_PDL")) c->pdl_enabled = atoi(e) != 0;
     if (const char* e = getenv("CUTESV_B200_GATHER")) c->p2p_enabled = strcmp(e, "nccl") != 0;
     if (const char* e = getenv("CUTESV_B200_BUCKET_SORT")) c->bucket_sort_enabled = atoi(e) != 0;
     if (const char* e = getenv("CUTESV_B200_RECORDS")) c->records_enabled = atoi(e) != 0;
@@ -444,7 +466,7 @@ extern "C" int csv_destroy(csv_ctx* c) {
                    &c->dr, &c->has_rows, &c->gl_table, &c->pow_half, &c->small.k_rid, &c->small.k_b, &c->small.k_prim,
                    &c->small.perm_a, &c->small.perm_b, &c->small.sel, &c->small.u_chrom, &c->small.u_a, &c->small.u_b,
                    &c->small.u_rid, &c->small.u_c, &c->boff, &c->rec_a, &c->rec_b, &c->recc_a, &c->recc_b, &c->big_bkt, &c->d_epoch,
-                   &c->d_len_eff, &c->g_send, &c->g_recv, &c->g_cand, &c->g_geno, &c->g_names, &c->g_scratch, &c->cal_in0, &c->cal_in1,
+                   &c->d_len_eff, &c->g_send, &c->g_recv, &c->g_cand, &c->g_geno, &c->g_names, &c->g_scratch, &c->g_tab, &c->cal_in0, &c->cal_in1,
                    &c->cal_out, &c->aln_flag, &c->scan_carry, &c->win_rec, &c->rest_list, &c->emit_cursor};
     for (DBuf* b : all) b->release();
     for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -814,8 +836,12 @@ static int run_segment_and_cluster(csv_ctx* c, TypeJob& J, int t, uint32_t kslot
                 J.small_list = MR.small_list; J.n_small = MR.n_small; J.rest_list = MR.rest_list; J.n_rest = MR.n_rest;
             }
         }
-        LAUNCH(c, k_select_heads, grid_for(c, J.n_host, SEL_TILE, 4), SEL_THREADS, 0, J, c->kept[t].as<uint32_t>(), c->kept_cap[t],
-               &ctr->n_kept[t], ts, &ctr->status, (uint32_t)ST_LIST_OVERFLOW, MR);
+        if (c->prev_is_chain_kernel)   // directly behind k_bucket_fixup on this stream
+            LAUNCH_PDL(c, k_select_heads, grid_for(c, J.n_host, SEL_TILE, 4), SEL_THREADS, 0, J, c->kept[t].as<uint32_t>(), c->kept_cap[t],
+                       &ctr->n_kept[t], ts, &ctr->status, (uint32_t)ST_LIST_OVERFLOW, MR);
+        else
+            LAUNCH(c, k_select_heads, grid_for(c, J.n_host, SEL_TILE, 4), SEL_THREADS, 0, J, c->kept[t].as<uint32_t>(), c->kept_cap[t],
+                   &ctr->n_kept[t], ts, &ctr->status, (uint32_t)ST_LIST_OVERFLOW, MR);
     } else {
         J.iv.rec = nullptr; J.iv.recc = nullptr;   // generic path: members are gathered by the cluster kernels
         HeadPred hp{J};
@@ -847,8 +873,8 @@ static int run_segment_and_cluster(csv_ctx* c, TypeJob& J, int t, uint32_t kslot
             CU(cudaEventRecord(c->ev_side_fork[t == CSV_INS ? 1 : 0], c->stream));
             CU(cudaStreamWaitEvent(side, c->ev_side_fork[t == CSV_INS ? 1 : 0], 0));
         }
-        if (t == CSV_INS) LAUNCH_NAMED(c, "k_cluster_small<INS>", (k_cluster_small<true>), c->n_sm * 6, 256, 0, JS, E, ctr, work_s, n_rest);
-        else LAUNCH_NAMED(c, "k_cluster_small<DEL>", (k_cluster_small<false>), c->n_sm * 6, 256, 0, JS, E, ctr, work_s, n_rest);
+        if (t == CSV_INS) LAUNCH_PDL_NAMED(c, "k_cluster_small<INS>", (k_cluster_small<true>), c->n_sm * 6, 256, 0, JS, E, ctr, work_s, n_rest);
+        else LAUNCH_PDL_NAMED(c, "k_cluster_small<DEL>", (k_cluster_small<false>), c->n_sm * 6, 256, 0, JS, E, ctr, work_s, n_rest);
         if (!J.small_list) { J.rest_list = JS.rest_list; J.n_rest = n_rest; }
     } else { J.small_list = nullptr; J.n_small = nullptr; J.rest_list = nullptr; J.n_rest = nullptr; }
     cudaStream_t lane_stream = c->stream;
@@ -914,7 +940,7 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
             const int g = (int)std::min<uint32_t>(n_tiles, (uint32_t)c->n_sm * 8);
             if (c->ticket_next >= (int)LB_ORDINALS) return set_err(CSV_E_STATE, "ticket pool exhausted");
             uint32_t* done_ctr = c->tickets.as<uint32_t>() + c->ticket_next++;
-#define BP_LAUNCH(RB) LAUNCH(c, (k_bucket_prefix<RB>), g, 256, 0, c->bkt.as<uint32_t>(), n_buckets, rb, (uint32_t)J.cp.min_support, bpre, tile_base, BB, &ctr->status, done_ctr, n_pass)
+#define BP_LAUNCH(RB) LAUNCH_PDL(c, (k_bucket_prefix<RB>), g, 256, 0, c->bkt.as<uint32_t>(), n_buckets, rb, (uint32_t)J.cp.min_support, bpre, tile_base, BB, &ctr->status, done_ctr, n_pass)
             switch (rb) {
                 case 1: BP_LAUNCH(1); break; case 2: BP_LAUNCH(2); break; case 3: BP_LAUNCH(3); break; case 4: BP_LAUNCH(4); break;
                 case 5: BP_LAUNCH(5); break; case 6: BP_LAUNCH(6); break; case 7: BP_LAUNCH(7); break; case 8: BP_LAUNCH(8); break;
@@ -923,11 +949,11 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
 #undef BP_LAUNCH
         }
         uint2* pairs = (uint2*)c->keys_a.p;   // 8 B per signature (ensure_lane_scratch)
-        LAUNCH(c, k_indel_scatter, grid_for(c, n, 256 * 4), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), n, t == CSV_INS ? 1 : 0, ct,
+        LAUNCH_PDL(c, k_indel_scatter, grid_for(c, n, 256 * 4), 256, 0, s.chrom.as<int32_t>(), s.a.as<int32_t>(), n, t == CSV_INS ? 1 : 0, ct,
                (const uint32_t*)bpre, (const uint32_t*)tile_base, c->bkt.as<uint32_t>(), pairs);
         stage_end(c, CSV_ST_KEYS);
         stage_begin(c, CSV_ST_SORT);
-        LAUNCH(c, k_bucket_fixup, grid_for(c, n, FX_TILE, 8), 256, 0, (const uint2*)pairs, n_pass, c->keys_b.as<uint32_t>(),
+        LAUNCH_PDL(c, k_bucket_fixup, grid_for(c, n, FX_TILE, 8), 256, 0, (const uint2*)pairs, n_pass, c->keys_b.as<uint32_t>(),
                c->vals_b.as<uint32_t>(), c->bkt.as<uint32_t>(), (int64_t)n_bkt, BB, (const uint32_t*)tile_base);
         stage_end(c, CSV_ST_SORT);
         J.n_dev = n_pass;
@@ -986,7 +1012,10 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
     }
     J.iv.is_ins = t == CSV_INS ? 1 : 0;
     J.small_path = c->small_path_enabled ? 1 : 0;
-    return run_segment_and_cluster(c, J, t, kslot_base);
+    c->prev_is_chain_kernel = bucket_sort;
+    rc = run_segment_and_cluster(c, J, t, kslot_base);
+    c->prev_is_chain_kernel = false;
+    return rc;
 }
 
 static int run_other(csv_ctx* c, int t, uint32_t kslot_base) {
@@ -1236,14 +1265,17 @@ static int enqueue_cluster(csv_ctx* c, uint32_t type_mask) {
             TileSync ts;
             rc = make_sync(c, (size_t)(c->kept_cap[t] / SEL_TILE + 2), &ts);
             if (rc) return rc;
-            LAUNCH(c, (k_scan_excl<8>), grid_for(c, std::max<int64_t>(c->kept_cap[t], 1), SEL_TILE, 2), SEL_THREADS, 0, c->cnt.as<uint32_t>() + kb,
-                   (int64_t)c->kept_cap[t], (const uint32_t*)&ctr->n_kept[t], prev < 0 ? (const uint32_t*)nullptr : (const uint32_t*)(carry + prev),
-                   carry + t, ts);
+            if (prev >= 0)
+                LAUNCH_PDL(c, (k_scan_excl<8>), grid_for(c, std::max<int64_t>(c->kept_cap[t], 1), SEL_TILE, 2), SEL_THREADS, 0, c->cnt.as<uint32_t>() + kb,
+                           (int64_t)c->kept_cap[t], (const uint32_t*)&ctr->n_kept[t], (const uint32_t*)(carry + prev), carry + t, ts);
+            else
+                LAUNCH(c, (k_scan_excl<8>), grid_for(c, std::max<int64_t>(c->kept_cap[t], 1), SEL_TILE, 2), SEL_THREADS, 0, c->cnt.as<uint32_t>() + kb,
+                       (int64_t)c->kept_cap[t], (const uint32_t*)&ctr->n_kept[t], (const uint32_t*)nullptr, carry + t, ts);
             kb += c->kept_cap[t];
             prev = t;
         }
         // final order; the same pass counts the genotype windows per bin
-        LAUNCH(c, k_permute, grid_for(c, c->cap_cand, 256, 4), 256, 0, c->cand_tmp.as<csv_cand>(), c->cnt.as<uint32_t>(), ctr, c->cap_cand,
+        LAUNCH_PDL(c, k_permute, grid_for(c, c->cap_cand, 256, 4), 256, 0, c->cand_tmp.as<csv_cand>(), c->cnt.as<uint32_t>(), ctr, c->cap_cand,
                c->cand.as<csv_cand>(), G, c->emit_cursor.as<unsigned long long>());
     }
     stage_end(c, CSV_ST_ORDER);
@@ -1254,11 +1286,13 @@ static int enqueue_cluster(csv_ctx* c, uint32_t type_mask) {
     {
         if (c->P.genotype) {
             TileSync ts;
-            rc = make_sync(c, (size_t)((G.n_bins + 1) / SEL_TILE + 2), &ts);
+            // 1024-bin tiles, one 128-bit access per thread: the scan of the (at most 2^20 + 2) bins is a latency chain,
+            // many small tiles on all SMs finish it sooner than few wide ones
+            rc = make_sync(c, (size_t)((G.n_bins + 1) / (SEL_THREADS * 4) + 2), &ts);
             if (rc) return rc;
-            LAUNCH(c, (k_scan_excl<32>), grid_for(c, G.n_bins + 1, SEL_THREADS * 32, 2), SEL_THREADS, 0, G.bin_start, (int64_t)G.n_bins + 1,
+            LAUNCH_PDL(c, (k_scan_excl<4>), grid_for(c, G.n_bins + 1, SEL_THREADS * 4, 4), SEL_THREADS, 0, G.bin_start, (int64_t)G.n_bins + 1,
                    (const uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, ts);
-            LAUNCH(c, (k_windows<1>), grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
+            LAUNCH_PDL(c, (k_windows<1>), grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
             if (c->n_reads > 0) {
                 PairBuf PB;
                 PB.cap = (uint32_t)std::min<int64_t>(4 * c->n_reads + (1 << 20), (int64_t)1 << 30);
@@ -1268,19 +1302,19 @@ static int enqueue_cluster(csv_ctx* c, uint32_t type_mask) {
                 PB.pairs4 = c->pairs.as<uint4>();
                 PB.count = &ctr->n_windows;
                 if (G.lin32) {
-                    LAUNCH(c, (k_reads_pass<true>), grid_for(c, c->n_reads, 1024, 8), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                    LAUNCH_PDL(c, (k_reads_pass<true>), grid_for(c, c->n_reads, 1024, 8), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
                            c->r_end.as<int32_t>(), c->r_id.as<int32_t>(), c->r_prim.as<uint8_t>(), c->n_reads, &ctr->status);
-                    LAUNCH(c, (k_pairs_test<true>), c->n_sm * 8, 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                    LAUNCH_PDL(c, (k_pairs_test<true>), c->n_sm * 8, 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
                            c->r_end.as<int32_t>(), c->r_id.as<int32_t>());
                 } else {
-                    LAUNCH(c, (k_reads_pass<false>), grid_for(c, c->n_reads, 1024, 8), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                    LAUNCH_PDL(c, (k_reads_pass<false>), grid_for(c, c->n_reads, 1024, 8), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
                            c->r_end.as<int32_t>(), c->r_id.as<int32_t>(), c->r_prim.as<uint8_t>(), c->n_reads, &ctr->status);
-                    LAUNCH(c, (k_pairs_test<false>), c->n_sm * 8, 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                    LAUNCH_PDL(c, (k_pairs_test<false>), c->n_sm * 8, 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
                            c->r_end.as<int32_t>(), c->r_id.as<int32_t>());
                 }
             }
         }
-        LAUNCH(c, k_finalize, grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
+        LAUNCH_PDL(c, k_finalize, grid_for(c, c->cap_cand, 256, 4), 256, 0, G);
         if (c->P.genotype && c->n_aln > 0 && (type_mask >> CSV_TRA & 1) && c->sig[CSV_TRA].n > 0) {
             AlnView A{c->a_chrom.as<int32_t>(), c->a_start.as<int32_t>(), c->a_end.as<int32_t>(), c->a_id.as<int32_t>(), c->a_prim.as<uint8_t>(),
                       c->a_off.as<uint32_t>(), c->a_span.as<int32_t>(), c->d_len.as<int64_t>()};

@@ -10,6 +10,14 @@
 
 namespace csv {
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its stream predecessor still runs; it must not touch memory before pdl_wait(), which returns once
+// the predecessor grid has completed and its writes are visible.  pdl_launch_dependents() lets the NEXT kernel do the same
+// with respect to this one.  Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+
 static constexpr uint32_t LB_LOCAL = 1u << 30;
 static constexpr uint32_t LB_INCL = 2u << 30;
 static constexpr uint32_t LB_MASK = (1u << 30) - 1;
@@ -181,6 +189,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(Pred pred, int64_t n_hos
 template <int ITEMS>
 __global__ void __launch_bounds__(SEL_THREADS) k_scan_excl(uint32_t* arr, int64_t n_host, const uint32_t* n_dev, const uint32_t* carry_in,
                                                            uint32_t* total_out, TileSync ts) {
+    pdl_launch_dependents(); pdl_wait();   // programmatic dependent launch: resident early, starts when the previous kernel has finished
     constexpr int TILE = SEL_THREADS * ITEMS;
     __shared__ uint32_t s_warp[9];
     __shared__ uint32_t s_tile, s_excl;
@@ -200,10 +209,17 @@ __global__ void __launch_bounds__(SEL_THREADS) k_scan_excl(uint32_t* arr, int64_
         if (base >= n) break;
         const int64_t i0 = base + (int64_t)threadIdx.x * ITEMS;
         uint32_t v[ITEMS], cnt = 0;
+        const bool vec = ITEMS == 4 && (((uintptr_t)arr) & 15) == 0 && i0 + ITEMS <= n;   // one coalesced 128-bit access per thread
+        if (vec) {
+            const uint4 x = *reinterpret_cast<const uint4*>(arr + i0);
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+            cnt = x.x + x.y + x.z + x.w;
+        } else {
 #pragma unroll
-        for (int j = 0; j < ITEMS; j++) {
-            v[j] = (i0 + j < n) ? arr[i0 + j] : 0u;
-            cnt += v[j];
+            for (int j = 0; j < ITEMS; j++) {
+                v[j] = (i0 + j < n) ? arr[i0 + j] : 0u;
+                cnt += v[j];
+            }
         }
         uint32_t total;
         const uint32_t local = block_excl_scan_256(cnt, s_warp, &total);
@@ -216,10 +232,13 @@ __global__ void __launch_bounds__(SEL_THREADS) k_scan_excl(uint32_t* arr, int64_
         }
         __syncthreads();
         uint32_t run = carry + s_excl + local;
+        if (vec) *reinterpret_cast<uint4*>(arr + i0) = make_uint4(run, run + v[0], run + v[0] + v[1], run + v[0] + v[1] + v[2]);
+        else {
 #pragma unroll
-        for (int j = 0; j < ITEMS; j++) {
-            if (i0 + j < n) arr[i0 + j] = run;
-            run += v[j];
+            for (int j = 0; j < ITEMS; j++) {
+                if (i0 + j < n) arr[i0 + j] = run;
+                run += v[j];
+            }
         }
         __syncthreads();
     }

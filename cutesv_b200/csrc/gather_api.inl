@@ -176,6 +176,7 @@ __device__ __forceinline__ int64_t gm_bound(const MergeJob& M, int r, int64_t k)
     return lo;
 }
 __global__ void __launch_bounds__(256) k_gather_merge(MergeJob M) {
+    pdl_launch_dependents(); pdl_wait();   // programmatic dependent launch: resident early, starts when the previous kernel has finished
     extern __shared__ uint32_t s_gm[];   // table path: [n_keys] exclusive offset of every key group, then [world * n_keys] of every (rank, key)
     __shared__ uint32_t s_warp[9];
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
@@ -275,32 +276,71 @@ __global__ void __launch_bounds__(256) k_gather_merge(MergeJob M) {
 
 // ---- peer-to-peer all-gather: no NCCL call in the step -------------------------------------------------------------------
 // Every rank owns a mail box (2 buffers x world slots + arrival flags) that all peers map through CUDA IPC.  A step's gather is
-// one kernel that stores the packed message into slot [rank] of every peer's box over NVLink / NVSwitch and, when the last
+// one kernel that packs the message straight into slot [rank] of every peer's box over NVLink / NVSwitch and, when the last
 // CTA has finished (system-scope fence), releases flag [rank] = epoch in every box; the merge kernel of each rank waits for
 // the world's flags.  Two buffers alternate by step: a rank can only be one step ahead of a peer (its merge of step k
 // waited for that peer's flag of step k), so a slot is never overwritten while its owner still reads it.
-struct PushJob {
-    const char* msg; int64_t msg_bytes; int world;
-    char* const* slots;                  // [world] this rank's slot in every peer's current buffer
-    unsigned long long* const* flags;    // [world] this rank's flag in every peer's current buffer
-    unsigned long long epoch;
-    uint32_t* done;
+// pack + push in ONE kernel: every 16 B word of the message is read once from the result arrays and stored straight into
+// slot [rank] of every box (own box included); no staging copy of the message, no separate clear of the key table.
+// The (first, end) key table is the one part that needs two phases (boundaries are found by the threads that copy the
+// records): it is built in a rank-local table, and the CTA that finishes last copies it into the boxes, clears the local
+// table for the next step (zero when allocated) and releases the flags.
+struct PackPushJob {
+    const csv_cand* cand; const csv_geno* geno; const int32_t* names; const Counters* ctr;
+    uint32_t cap_cand, cap_names;
+    GatherLayout L; int rank, world;
+    uint2* tab_local;                    // [L.n_keys], all zero between steps
+    char* const* slots; unsigned long long* const* flags; unsigned long long epoch; uint32_t* done;
 };
-__global__ void __launch_bounds__(256) k_gather_push(PushJob J) {
+__global__ void __launch_bounds__(256) k_gather_pack_push(PackPushJob J) {
+    pdl_launch_dependents();   // the next kernel of the chain may become resident now (it waits for this grid to finish)
     __shared__ uint32_t s_last;
-    const int64_t n16 = J.msg_bytes / 16;
-    const uint4* src = (const uint4*)J.msg;
+    const GatherLayout& L = J.L;
+    const int W = J.world;
+    const int64_t nc = min(J.ctr->n_cand, J.cap_cand), nn = min(J.ctr->n_names, J.cap_names);
+    const int64_t cc = nc < L.pad_cand ? nc : L.pad_cand, cn = nn < L.pad_names ? nn : L.pad_names;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = tid; i < n16; i += stride) {
-        const uint4 v = src[i];
-        for (int p = 0; p < J.world; p++) ((uint4*)J.slots[p])[i] = v;
+    if (tid < W) {
+        int64_t* h = (int64_t*)J.slots[tid];
+        h[0] = nc; h[1] = nn; h[2] = (nc > L.pad_cand || nn > L.pad_names) ? 1 : 0; h[3] = J.rank;
+    }
+    const uint4* src_c = (const uint4*)J.cand;
+    for (int64_t i = tid; i < cc * 4; i += stride) {
+        const uint4 v = src_c[i];
+        for (int p = 0; p < W; p++) ((uint4*)(J.slots[p] + GH_WORDS * 8))[i] = v;
+    }
+    if (L.n_keys) {
+        const int32_t nct = L.n_keys / CSV_NTYPES;
+        for (int64_t i = tid; i < cc; i += stride) {
+            const int32_t sv = J.cand[i].svtype, ch = J.cand[i].chrom;
+            if (sv < 0 || sv >= CSV_NTYPES || ch < 0 || ch >= nct) continue;
+            const int32_t k = sv * nct + ch;
+            if (i == 0 || J.cand[i - 1].svtype != sv || J.cand[i - 1].chrom != ch) J.tab_local[k].x = (uint32_t)i;
+            if (i + 1 == cc || J.cand[i + 1].svtype != sv || J.cand[i + 1].chrom != ch) J.tab_local[k].y = (uint32_t)(i + 1);
+        }
+    }
+    const uint2* src_g = (const uint2*)J.geno;
+    for (int64_t i = tid; i < cc * 5; i += stride) {
+        const uint2 v = src_g[i];
+        for (int p = 0; p < W; p++) ((uint2*)(J.slots[p] + L.off_geno))[i] = v;
+    }
+    for (int64_t i = tid; i < cn; i += stride) {
+        const int32_t v = J.names[i];
+        for (int p = 0; p < W; p++) ((int32_t*)(J.slots[p] + L.off_names))[i] = v;
     }
     __threadfence_system();
     if (threadIdx.x == 0) s_last = atomicAdd(J.done, 1u) == gridDim.x - 1 ? 1u : 0u;
     __syncthreads();
     if (!s_last) return;
+    __threadfence();
+    for (int k = threadIdx.x; k < L.n_keys; k += blockDim.x) {
+        const uint2 e = __ldcg(&J.tab_local[k]);
+        for (int p = 0; p < W; p++) ((uint2*)(J.slots[p] + L.off_tab))[k] = e;
+        J.tab_local[k] = make_uint2(0u, 0u);
+    }
     __threadfence_system();
-    if ((int)threadIdx.x < J.world) {
+    __syncthreads();
+    if ((int)threadIdx.x < W) {
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(J.flags[threadIdx.x]), "l"(J.epoch) : "memory");
     }
     if (threadIdx.x == 0) *J.done = 0u;   // ready for the next step (stream order)
@@ -389,10 +429,6 @@ static int gather_enqueue(csv_ctx* c) {
     CU(c->g_cand.ensure((size_t)L.pad_cand * W * sizeof(csv_cand) + 64));
     CU(c->g_geno.ensure((size_t)L.pad_cand * W * sizeof(csv_geno) + 64));
     CU(c->g_names.ensure((size_t)L.pad_names * W * 4 + 64));
-    // pack -> ONE ncclAllGather -> merge: three launches and one small D2H copy per step
-    if (L.n_keys) CU(cudaMemsetAsync(c->g_send.as<char>() + L.off_tab, 0, (size_t)L.n_keys * 8, c->stream));
-    LAUNCH(c, k_gather_pack, c->n_sm * 2, 256, 0, c->cand.as<csv_cand>(), c->geno.as<csv_geno>(), c->names.as<int32_t>(),
-           c->counters.as<Counters>(), c->cap_cand, c->cap_names, L, c->rank, c->g_send.as<char>());
     csv_ctx::P2PState& X = c->p2p;
     const bool want_p2p = c->p2p_enabled && !X.failed && W > 1;
     if (want_p2p && (!X.ready || X.slot_bytes != L.msg_bytes)) {   // first gather / the padding changed: collective re-setup
@@ -401,20 +437,29 @@ static int gather_enqueue(csv_ctx* c) {
     }
     MergeJob M;
     if (want_p2p && X.ready) {
-        // pack -> push into every peer's mail box -> merge (which waits for the world's flags): no NCCL call in the step
+        // (pack + push into every peer's mail box) -> merge (which waits for the world's flags): two launches and one
+        // small D2H copy per step, no NCCL call
         X.epoch++;
         const int b = (int)(X.epoch & 1ull);
-        PushJob J;
-        J.msg = c->g_send.as<char>(); J.msg_bytes = L.msg_bytes; J.world = W;
+        CU(c->g_tab.ensure((size_t)std::max<int64_t>(L.n_keys, 1) * 8, true));   // zero when allocated, re-zeroed by the kernel
+        PackPushJob J;
+        J.cand = c->cand.as<csv_cand>(); J.geno = c->geno.as<csv_geno>(); J.names = c->names.as<int32_t>();
+        J.ctr = c->counters.as<Counters>(); J.cap_cand = c->cap_cand; J.cap_names = c->cap_names;
+        J.L = L; J.rank = c->rank; J.world = W;
+        J.tab_local = c->g_tab.as<uint2>();
         J.slots = (char* const*)((void**)X.d_tab.p + (size_t)b * W);
         J.flags = (unsigned long long* const*)((void**)X.d_tab.p + (size_t)(2 + b) * W);
         J.epoch = X.epoch;
         J.done = (uint32_t*)((void**)X.d_tab.p + (size_t)4 * W);
-        LAUNCH(c, k_gather_push, std::min(c->n_sm, (int)std::max<int64_t>(L.msg_bytes / 16 / 256, 1)), 256, 0, J);
+        LAUNCH(c, k_gather_pack_push, std::min(c->n_sm * 2, (int)std::max<int64_t>(L.msg_bytes / 16 / 256, 1)), 256, 0, J);
         M.recv = (const char*)X.box + (size_t)b * W * L.msg_bytes;
         M.flags = (const unsigned long long*)((const char*)X.box + X.flags_off) + (size_t)b * W;
         M.epoch = X.epoch;
     } else {
+        // clear the key table -> pack -> ONE ncclAllGather -> merge
+        if (L.n_keys) CU(cudaMemsetAsync(c->g_send.as<char>() + L.off_tab, 0, (size_t)L.n_keys * 8, c->stream));
+        LAUNCH(c, k_gather_pack, c->n_sm * 2, 256, 0, c->cand.as<csv_cand>(), c->geno.as<csv_geno>(), c->names.as<int32_t>(),
+               c->counters.as<Counters>(), c->cap_cand, c->cap_names, L, c->rank, c->g_send.as<char>());
         NC(g_nccl.AllGather(c->g_send.p, c->g_recv.p, (size_t)L.msg_bytes, ncclUint8, c->comm, c->stream));
         M.recv = c->g_recv.as<char>();
         M.flags = nullptr; M.epoch = 0;
@@ -425,7 +470,8 @@ static int gather_enqueue(csv_ctx* c) {
     M.hdr = c->g_scratch.as<int64_t>();
     const size_t gm_smem = (size_t)L.n_keys * (W + 1) * 4;
     if (gm_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_gather_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm_smem));
-    LAUNCH(c, k_gather_merge, grid_for(c, std::max<int64_t>(L.pad_cand * W, L.pad_names), 256, 2), 256, gm_smem, M);
+    if (M.flags) LAUNCH_PDL(c, k_gather_merge, grid_for(c, std::max<int64_t>(L.pad_cand * W, L.pad_names), 256, 2), 256, gm_smem, M);   // behind k_gather_pack_push
+    else LAUNCH(c, k_gather_merge, grid_for(c, std::max<int64_t>(L.pad_cand * W, L.pad_names), 256, 2), 256, gm_smem, M);
     CU(cudaMemcpyAsync(c->h_gather, M.hdr, (size_t)(W * GH_WORDS + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     c->gathered = true;
     return CSV_OK;

@@ -319,7 +319,7 @@ int64_t csv_graph_replays(csv_ctx* ctx);
 /* ---- multi-GPU: contigs sharded over ranks, one csv_ctx per GPU / process -------------------------------------
  * Every resolution_* call of the reference is keyed by (svtype, chr) and reads only that contig's signatures and
  * reads-table rows (cuteSV:1116-1189; resolveINDEL.py:52-54,445-447), so contigs are independent units: each rank
- * runs the whole pipeline on its contigs with no data-path collective, and ONE NCCL all-gather of the final
+ * runs the whole pipeline on its contigs with no data-path collective, and ONE all-gather of the final
  * records assembles the result on every rank in the single-GPU order.  (The reference's Pool(threads).map_async
  * over (type, chr) tasks, cuteSV:1113-1199, is the CPU counterpart.) */
 
@@ -335,8 +335,8 @@ int csv_comm_destroy(csv_ctx* ctx);
 /* After csv_cluster, asynchronous on the ctx stream, collective: packs this rank's records (csv_cand, csv_geno,
  * supporting read ids) into one padded message, gathers the messages of all ranks, then merges them on the device
  * into the single-GPU order (svtype, contig id, emission order).  The gather itself is either ONE ncclAllGather over
- * NVLink or (default when every rank could map every rank's mail box through CUDA IPC) ONE kernel that stores the
- * message into the peers' mail boxes over NVLink and releases an arrival flag; csv_set_gather(ctx, 0) or
+ * NVLink or (default when every rank could map every rank's mail box through CUDA IPC) ONE kernel that packs the
+ * records straight into the peers' mail boxes over NVLink and releases an arrival flag (no staging copy); csv_set_gather(ctx, 0) or
  * CUTESV_B200_GATHER=nccl selects NCCL, csv_gather_mode() tells which one the last gather used (1 peer-to-peer).  csv_cand.reserved[1] of a
  * gathered record is its source rank (csv_cand.aux of an INS row indexes THAT rank's INS signatures).  The padded
  * message size is agreed once (first call: one count all-reduce) and re-agreed only when a rank outgrows it. */
