@@ -58,6 +58,8 @@ def lib():
         L.bamr_name_ranks.argtypes = [C.c_void_p, _I32P]
         L.bamr_decode_seq.argtypes = [C.c_void_p, C.c_int64, C.c_char_p]
         L.bamr_index_stats.argtypes = [C.c_char_p, C.c_int32, _I64P]
+        L.bamr_unpack_ranges.argtypes = [C.c_void_p, C.c_int64, _I64P, _I64P, _I64P, C.c_void_p]
+        L.bamr_unpack_ranges.restype = None
         _lib = L
     return _lib
 
@@ -146,34 +148,62 @@ class BamReader(object):
         return r
 
 
+# BAM packs two bases per byte (high nibble first, "=ACMGRSVTWYHKDBN"): one 16-bit table look-up per byte
+_NIB = "=ACMGRSVTWYHKDBN"
+_LUT16 = np.array([ord(_NIB[b >> 4]) | (ord(_NIB[b & 15]) << 8) for b in range(256)], dtype="<u2")
+
+
 def decode_seq(packet, rec):
     """Query sequence (ASCII) of record `rec` of a packet."""
     l_seq = int(packet["query_len"][rec])
-    o = int(packet["seq_off"][rec])
-    if int(packet["seq_off"][rec + 1]) - o < (l_seq + 1) // 2:
+    if "seq_lo" in packet:   # a subset that still refers to the bases of its parent packet (subset_packet)
+        o, end = int(packet["seq_lo"][rec]), int(packet["seq_hi"][rec])
+    else:
+        o, end = int(packet["seq_off"][rec]), int(packet["seq_off"][rec + 1])
+    if end - o < (l_seq + 1) // 2:
         return ""
-    buf = C.create_string_buffer(l_seq)
-    src = packet["seq4"][o:o + (l_seq + 1) // 2]
-    lib().bamr_decode_seq(src.ctypes.data_as(C.c_void_p), l_seq, buf)
-    return buf.raw.decode()
+    return _LUT16[packet["seq4"][o:o + (l_seq + 1) // 2]].view(np.uint8)[:l_seq].tobytes().decode("ascii")
+
+
+def unpack_ranges(seq4, nib0, length, out_off, total):
+    """ASCII bases of many ranges of BAM's 4-bit packed bases in one C call (range i: `length[i]` bases from nibble `nib0[i]`)."""
+    out = np.empty(int(total), dtype=np.uint8)
+    n = len(nib0)
+    if n and total:
+        seq4 = np.ascontiguousarray(seq4, dtype=np.uint8)
+        nib0, length, out_off = (np.ascontiguousarray(x, dtype=np.int64) for x in (nib0, length, out_off))
+        lib().bamr_unpack_ranges(seq4.ctypes.data_as(C.c_void_p), n, nib0.ctypes.data_as(_I64P), length.ctypes.data_as(_I64P),
+                                 out_off.ctypes.data_as(_I64P), out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 def subset_packet(pk, keep):
-    """Rows `keep` (index array, ascending) of a packet, CSR arrays rebuilt."""
+    """Rows `keep` (index array, ascending) of a packet, CSR arrays rebuilt.  The kept rows form few long runs (the scan drops
+    a few percent of the records), so the variable-length parts are copied run by run, not element by element."""
     keep = np.asarray(keep, dtype=np.int64)
+    n = len(pk["chrom"])
+    if len(keep) == n:
+        return pk
     out = {k: pk[k][keep] for k in ("chrom", "ref_start", "ref_end", "flag", "mapq", "query_len", "read_id")}
+    if len(keep):
+        brk = np.flatnonzero(np.diff(keep) != 1)
+        run_a = keep[np.concatenate([[0], brk + 1])]
+        run_b = keep[np.concatenate([brk, [len(keep) - 1]])] + 1
+    else:
+        run_a = run_b = np.zeros(0, dtype=np.int64)
 
-    def regather(off):
+    def regather(off, arrays):
         lens = (off[1:] - off[:-1])[keep]
         new_off = np.zeros(len(keep) + 1, dtype=np.int64)
         np.cumsum(lens, out=new_off[1:])
-        idx = np.repeat(off[:-1][keep] - new_off[:-1], lens) + np.arange(int(new_off[-1]), dtype=np.int64)
-        return new_off, idx
-    out["cigar_off"], ci = regather(pk["cigar_off"])
-    out["cigar"] = pk["cigar"][ci]
-    out["sa_off"], si = regather(pk["sa_off"])
-    out["sa"] = {k: v[si] for k, v in pk["sa"].items()}
-    if "seq_off" in pk:
-        out["seq_off"], qi = regather(pk["seq_off"])
-        out["seq4"] = pk["seq4"][qi]
+        lo, hi = off[run_a].tolist(), off[run_b].tolist()
+        return new_off, [np.concatenate([v[x:y] for x, y in zip(lo, hi)]) if len(lo) else v[:0] for v in arrays]
+    out["cigar_off"], (out["cigar"],) = regather(pk["cigar_off"], [pk["cigar"]])
+    keys = list(pk["sa"].keys())
+    out["sa_off"], vals = regather(pk["sa_off"], [pk["sa"][k] for k in keys])
+    out["sa"] = dict(zip(keys, vals))
+    if "seq_off" in pk:   # the packed bases are not copied: only the host reads them (decode_seq), through the parent's offsets
+        out["seq4"] = pk["seq4"]
+        out["seq_lo"] = pk["seq_off"][:-1][keep]
+        out["seq_hi"] = pk["seq_off"][1:][keep]
     return out

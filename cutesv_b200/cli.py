@@ -123,7 +123,7 @@ class _Accumulator(object):
 
     def __init__(self, eng, min_siglength, merge_ins_threshold):
         self.eng = eng
-        self.ins_seq = []
+        self.ins_seq = packing.InsStore()   # INS sequence of every INS signature, by input index
         self.rec_base = 0
         self.name_id = {}
         self.names = []
@@ -144,7 +144,9 @@ class _Accumulator(object):
 
     def extract(self, packet, n_records, query_of, want_seq, cigar_of=None):
         """One packet through csv_extract_append.  query_of(rec) -> query sequence of packet record `rec`;
-        cigar_of(rec) -> (uint32 CIGAR array, reference_start) for the rare signatures the host rebuilds."""
+        cigar_of(rec) -> (uint32 CIGAR array, reference_start) for the rare signatures the host rebuilds.
+        A packet of the native decoder carries BAM's packed bases: the INS sequences are then cut out of them for the
+        whole packet at once (packing.ins_block_from_packed), per-signature Python only for the exceptions."""
         t0 = time.perf_counter()
         r = self.eng.extract(packet, append=True)
         t1 = time.perf_counter()
@@ -153,11 +155,23 @@ class _Accumulator(object):
         if want_seq and n_new:
             po, pc, pieces = self.eng.fetch_ins_pieces(r["first"]["INS"], n_new, r["first_pieces"], r["n_pieces"] - r["first_pieces"])
             base = self.rec_base
-            for i in range(n_new):
-                self.ins_seq.append(packing.ins_sequence(pieces, int(po[i]), int(pc[i]), lambda rec: query_of(rec - base),
-                                                         (lambda rec: cigar_of(rec - base)) if cigar_of else None, self.merge))
+
+            def slow(i):
+                return packing.ins_sequence(pieces, int(po[i]), int(pc[i]), lambda rec: query_of(rec - base),
+                                            (lambda rec: cigar_of(rec - base)) if cigar_of else None, self.merge)
+            if "seq4" in packet:
+                local = np.array(pieces, dtype=np.int32, copy=True)
+                local[:, 0] -= base
+                lo, hi = (packet["seq_lo"], packet["seq_hi"]) if "seq_lo" in packet else (packet["seq_off"][:-1], packet["seq_off"][1:])
+                bases, off, rest = packing.ins_block_from_packed(local, po, pc, packet["seq4"], lo, hi, packet["query_len"])
+                first = len(self.ins_seq)
+                self.ins_seq.add_block(bases, off)
+                for i in rest.tolist():
+                    self.ins_seq[first + i] = slow(i)
+            else:
+                self.ins_seq.add_strings([slow(i) for i in range(n_new)])
         else:
-            self.ins_seq.extend([""] * n_new)
+            self.ins_seq.add_empty(n_new)
         self.rec_base += n_records
         self.t_ins_seq += time.perf_counter() - t1
 
@@ -426,7 +440,13 @@ class _NativeSource(object):
                     keep[m & ~hit] = False
             sub = bamio.subset_packet(pk, np.flatnonzero(keep))
             if len(sub["chrom"]):
-                acc.extract(sub, len(sub["chrom"]), lambda rec: bamio.decode_seq(sub, rec), want_seq,
+                last = [-1, ""]   # the INS signatures of one record follow each other: decode its query once
+
+                def query_of(rec, sub=sub, last=last):
+                    if last[0] != rec:
+                        last[0], last[1] = rec, bamio.decode_seq(sub, rec)
+                    return last[1]
+                acc.extract(sub, len(sub["chrom"]), query_of, want_seq,
                             lambda rec: (sub["cigar"][sub["cigar_off"][rec]:sub["cigar_off"][rec + 1]], int(sub["ref_start"][rec])))
             n_seen += len(keep)
             logging.info("Decoded %d records." % n_seen)

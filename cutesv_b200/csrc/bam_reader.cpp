@@ -576,6 +576,17 @@ void bamr_decode_seq(const uint8_t* seq4, int64_t l_seq, char* out) {
     for (int64_t i = 0; i < l_seq; i++) out[i] = tab[(seq4[i >> 1] >> ((~i & 1) << 2)) & 15];
 }
 
+// many base ranges at once: range i = `len[i]` bases starting at nibble `nib0[i]` of seq4, written as ASCII at out + out_off[i]
+// (the INS signature sequences of a whole packet, cutesv_b200/packing.py::ins_block_from_packed)
+void bamr_unpack_ranges(const uint8_t* seq4, int64_t n, const int64_t* nib0, const int64_t* len, const int64_t* out_off, char* out) {
+    static const char tab[] = "=ACMGRSVTWYHKDBN";
+    for (int64_t i = 0; i < n; i++) {
+        char* o = out + out_off[i];
+        const int64_t s = nib0[i];
+        for (int64_t k = 0; k < len[i]; k++) o[k] = tab[(seq4[(s + k) >> 1] >> ((~(s + k) & 1) << 2)) & 15];
+    }
+}
+
 // Per-reference mapped-read counts from a .bai index (get_index_statistics, cuteSV:1015-1025):
 // the pseudo-bin 37450 of every reference holds (n_mapped, n_unmapped).
 static int bamr_index_stats_impl(const char* bai_path, int32_t n_ref, int64_t* mapped) {

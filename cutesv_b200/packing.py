@@ -124,3 +124,93 @@ def ins_sequence(pieces, off, cnt, query_of, cigar_of=None, merge=None):
             q = revcomp(q)
         out.append(q[a:b])
     return "".join(out)
+
+
+class InsStore(object):
+    """INS signature sequences by input index, kept as a few large ASCII buffers (one block per packet: uint8 bases +
+    offsets) instead of one Python string per signature; a string is only materialised for the rows that need one (the
+    representative signature of an emitted candidate, members of a tie group, the work-dir writer).  Sequences the
+    vectorised builder does not cover, and rows moved by the tie ordering, live in an override table."""
+
+    def __init__(self):
+        self._first = []     # first input index of every block
+        self._blocks = []    # (bases uint8, offsets int64 [k + 1])
+        self._over = {}
+        self._n = 0
+
+    def __len__(self):
+        return self._n
+
+    def add_block(self, bases, offsets):
+        self._first.append(self._n)
+        self._blocks.append((bases, offsets))
+        self._n += len(offsets) - 1
+
+    def add_strings(self, strings):
+        off = np.zeros(len(strings) + 1, dtype=np.int64)
+        if len(strings):
+            np.cumsum(np.fromiter(map(len, strings), dtype=np.int64, count=len(strings)), out=off[1:])
+        self.add_block(np.frombuffer("".join(strings).encode("ascii"), dtype=np.uint8), off)
+
+    def add_empty(self, k):
+        self.add_block(np.zeros(0, dtype=np.uint8), np.zeros(k + 1, dtype=np.int64))
+
+    def __getitem__(self, k):
+        k = int(k)
+        v = self._over.get(k)
+        if v is not None:
+            return v
+        if not 0 <= k < self._n:
+            raise IndexError(k)
+        import bisect
+        b = bisect.bisect_right(self._first, k) - 1
+        bases, off = self._blocks[b]
+        j = k - self._first[b]
+        return bases[off[j]:off[j + 1]].tobytes().decode("ascii")
+
+    def __setitem__(self, k, v):
+        self._over[int(k)] = v
+
+    def __iter__(self):
+        for first, (bases, off) in zip(self._first, self._blocks):
+            whole = bases.tobytes().decode("ascii")
+            o = off.tolist()
+            for j in range(len(o) - 1):
+                v = self._over.get(first + j)
+                yield whole[o[j]:o[j + 1]] if v is None else v
+
+
+def ins_block_from_packed(pieces, po, pc, seq4, seq_lo, seq_hi, query_len):
+    """Vectorised rebuild of the INS sequences of one packet from BAM's 4-bit packed bases.
+    pieces: int32 [m, 4] = (packet record, a, b, rc); signature i = pieces po[i] .. po[i] + pc[i] (consecutive).
+    Covers forward-strand pieces with non-negative slice bounds (q[a:b], clamped like a Python slice); returns
+    (bases uint8, offsets int64 [n + 1], slow) where `slow` lists the signatures that need packing.ins_sequence
+    (reverse complement, merged-from-CIGAR marker pieces, negative slice indices): they take no room in `bases`."""
+    n = len(po)
+    m = len(pieces)
+    po = np.asarray(po, dtype=np.int64)
+    pc = np.asarray(pc, dtype=np.int64)
+    if n == 0:
+        return np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    contiguous = po[0] == 0 and bool(np.all(po[1:] == po[:-1] + pc[:-1])) and po[-1] + pc[-1] == m
+    if not contiguous:
+        return np.zeros(0, dtype=np.uint8), np.zeros(n + 1, dtype=np.int64), np.arange(n, dtype=np.int64)
+    rec = pieces[:, 0].astype(np.int64)
+    a = pieces[:, 1].astype(np.int64)
+    b = pieces[:, 2].astype(np.int64)
+    ql = np.asarray(query_len, dtype=np.int64)[rec]
+    lo = np.asarray(seq_lo, dtype=np.int64)[rec]
+    have = (np.asarray(seq_hi, dtype=np.int64)[rec] - lo) >= (ql + 1) // 2      # '*' query: every slice is empty
+    simple_piece = (pieces[:, 3] == 0) & (a >= 0) & (b >= 0)
+    sig_of_piece = np.repeat(np.arange(n, dtype=np.int64), pc)
+    bad_sig = np.zeros(n, dtype=bool)
+    bad_sig[sig_of_piece[~simple_piece]] = True
+    a2 = np.minimum(a, ql)
+    plen = np.where(have, np.maximum(np.minimum(b, ql) - a2, 0), 0)
+    plen[bad_sig[sig_of_piece]] = 0
+    pstart = np.zeros(m + 1, dtype=np.int64)
+    np.cumsum(plen, out=pstart[1:])
+    from . import bamio   # the unpacking loop is C (libcutesv_bam.so, the library the packed bases come from)
+    bases = bamio.unpack_ranges(seq4, 2 * lo + a2, plen, pstart[:-1], pstart[-1])
+    offsets = np.concatenate([pstart[po], pstart[-1:]])
+    return bases, offsets, np.flatnonzero(bad_sig)

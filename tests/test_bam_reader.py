@@ -100,8 +100,9 @@ def test_subset_packet(tmp_path):
         assert np.array_equal(sub[k], want[k]), k
     for k in want["sa"]:
         assert np.array_equal(sub["sa"][k], want["sa"][k]), k
-    for j in (0, len(keep) - 1):
+    for j in range(len(keep)):   # the subset reads the bases of its parent packet through (seq_lo, seq_hi)
         assert bamio.decode_seq(sub, j) == reads[keep[j]].query_sequence
+    assert bamio.subset_packet(pk, np.arange(len(pk["chrom"]))) is pk   # nothing dropped: no copy
     rd.close()
 
 
