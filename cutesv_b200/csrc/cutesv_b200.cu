@@ -95,6 +95,7 @@ struct ExtractState {
     uint32_t n_records = 0;          // alignment records of all packets of the accumulation (record index base of INS pieces)
     uint32_t n_skipped = 0;
     bool appending = false;
+    double per_record[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // largest yield of a packet so far: signatures per type [0..4], pieces [5] per alignment record
 };
 static void extract_release(ExtractState* x) {
     for (int k = 0; k < 7; k++) { x->r[k].release(); x->s[k].release(); }

@@ -72,6 +72,11 @@ static int extract_impl(csv_ctx* c, const csv_read_cols* reads, const uint32_t* 
     cap[CSV_INS] = (uint32_t)std::min<int64_t>((int64_t)base[CSV_INS] + 4 * n + 1024, lim);
     for (int t = CSV_INV; t < CSV_NTYPES; t++) cap[t] = (uint32_t)std::min<int64_t>((int64_t)base[t] + 2 * n_sa + n / 4 + 1024, lim);
     cap_pieces = (uint32_t)std::min<int64_t>((int64_t)base[5] + 8 * n + 2048, 2 * lim);
+    // later packets of a run: what the densest packet so far yielded per record, with head room (a rerun costs a second pass
+    // over the packet and a reallocation of every output column)
+    for (int t = 0; t < CSV_NTYPES; t++)
+        cap[t] = (uint32_t)std::min<int64_t>(std::max<int64_t>(cap[t], (int64_t)base[t] + (int64_t)(1.25 * X.per_record[t] * (double)n) + 1024), lim);
+    cap_pieces = (uint32_t)std::min<int64_t>(std::max<int64_t>(cap_pieces, (int64_t)base[5] + (int64_t)(1.25 * X.per_record[5] * (double)n) + 2048), 2 * lim);
     for (int attempt = 0; attempt < 3; attempt++) {
         ExtractOut O;
         memset(&O, 0, sizeof(O));
@@ -134,6 +139,10 @@ static int extract_impl(csv_ctx* c, const csv_read_cols* reads, const uint32_t* 
             c->sig[t].n = h[t];
             c->sig[t].has_c = (t == CSV_INS || t == CSV_INV || t == CSV_TRA);
             if (counts) counts[t] = h[t];
+        }
+        if (n > 0) {
+            for (int t = 0; t < CSV_NTYPES; t++) X.per_record[t] = std::max(X.per_record[t], (double)(h[t] - base[t]) / (double)n);
+            X.per_record[5] = std::max(X.per_record[5], (double)(h[5] - base[5]) / (double)n);
         }
         X.n_pieces = h[5];
         X.n_skipped += h[8];

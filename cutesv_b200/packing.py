@@ -194,7 +194,16 @@ def ins_block_from_packed(pieces, po, pc, seq4, seq_lo, seq_hi, query_len):
         return np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int64)
     contiguous = po[0] == 0 and bool(np.all(po[1:] == po[:-1] + pc[:-1])) and po[-1] + pc[-1] == m
     if not contiguous:
-        return np.zeros(0, dtype=np.uint8), np.zeros(n + 1, dtype=np.int64), np.arange(n, dtype=np.int64)
+        # the device hands out piece slots with atomics: a signature's pieces are consecutive, the signatures are in no
+        # particular order -> bring the pieces into signature order first
+        start = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(pc, out=start[1:])
+        order = np.repeat(po - start[:-1], pc) + np.arange(int(start[-1]), dtype=np.int64)
+        if len(order) and (order.min() < 0 or order.max() >= m):
+            return np.zeros(0, dtype=np.uint8), np.zeros(n + 1, dtype=np.int64), np.arange(n, dtype=np.int64)
+        pieces = np.asarray(pieces)[order]
+        po = start[:-1]
+        m = len(pieces)
     rec = pieces[:, 0].astype(np.int64)
     a = pieces[:, 1].astype(np.int64)
     b = pieces[:, 2].astype(np.int64)

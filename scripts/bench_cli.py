@@ -102,13 +102,32 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
         from emul_engine import EmulEngine
         engine = EmulEngine()
+    dev = {}
+    if "--profile" in sys.argv and engine is None:   # device-side split of csv_extract_append (CUDA events) beside its wall time
+        from cutesv_b200.engine import Engine
+        engine = Engine(0)
+        engine.set_profiling(True)
+        inner = engine.extract
+
+        def timed_extract(packed, append=False):
+            w0 = time.perf_counter()
+            r = inner(packed, append=append)
+            dev["wall_s"] = dev.get("wall_s", 0.0) + time.perf_counter() - w0
+            for k, v in engine.stage_ms().items():
+                if v:
+                    dev[k + "_ms"] = dev.get(k + "_ms", 0.0) + v
+            dev["calls"] = dev.get("calls", 0) + 1
+            dev["cigar_bytes"] = dev.get("cigar_bytes", 0) + int(packed["cigar"].nbytes)
+            return r
+        engine.extract = timed_extract
     t0 = time.perf_counter()
     cli.main_ctrl(a, argv, engine=engine)
     wall = time.perf_counter() - t0
     n_rec = sum(1 for line in open(out) if not line.startswith("#"))
     print(json.dumps(dict(n_records_in_bam=n_written, bam_mb=os.path.getsize(bam) / 1e6, bam_write_s=t_write, cli_wall_s=wall,
                           records_per_s=n_written / wall, vcf_records=n_rec, genotype="--genotype" in sys.argv,
-                          stages_s={k: round(v, 4) for k, v in cli.main_ctrl.last_stages.items()})))
+                          stages_s={k: round(v, 4) for k, v in cli.main_ctrl.last_stages.items()},
+                          extract_calls={k: (round(v, 3) if isinstance(v, float) else v) for k, v in dev.items()})))
 
 
 if __name__ == "__main__":

@@ -61,13 +61,24 @@ def test_ins_block_matches_python_slices():
         assert store[0] == "x" and store[1] == "yy"
 
 
-def test_ins_block_non_contiguous_pieces_fall_back():
-    queries, qlen, pieces, po, pc = _case(11, n_sig=20)
-    seq4, lo, hi = _pack(queries)
-    po2 = po.copy()
-    po2[5], po2[6] = po[6], po[5]
-    pc2 = pc.copy()
-    pc2[5], pc2[6] = pc[6], pc[5]
-    bases, off, rest = packing.ins_block_from_packed(pieces, po2, pc2, seq4, lo, hi, qlen)
-    if pc[5] != 0 and pc[6] != 0:
-        assert rest.tolist() == list(range(len(po))) and len(bases) == 0
+def test_ins_block_pieces_in_any_order():
+    """The device allocates piece slots with atomics: signatures' piece ranges come in no particular order."""
+    for seed in (11, 12):
+        queries, qlen, pieces, po, pc = _case(seed, n_sig=120)
+        seq4, lo, hi = _pack(queries)
+        want = [packing.ins_sequence(pieces, int(po[i]), int(pc[i]), lambda rec: queries[rec]) for i in range(len(po))]
+        rng = np.random.default_rng(seed)
+        perm = rng.permutation(len(po))          # shuffle the signatures' ranges inside the piece array (+ an unused slot)
+        new_pieces, new_po = [(0, 0, 0, 0)], np.zeros(len(po), dtype=np.int32)
+        for i in perm:
+            new_po[i] = len(new_pieces)
+            new_pieces.extend(pieces[po[i]:po[i] + pc[i]].tolist())
+        new_pieces = np.array(new_pieces, dtype=np.int32).reshape(-1, 4)
+        bases, off, rest = packing.ins_block_from_packed(new_pieces, new_po, pc, seq4, lo, hi, qlen)
+        store = packing.InsStore()
+        store.add_block(bases, off)
+        slow = set(rest.tolist())
+        assert len(slow) < len(po)
+        for i in range(len(po)):
+            if i not in slow:
+                assert store[i] == want[i], (seed, i)
