@@ -287,6 +287,15 @@ static int grid_for(const csv_ctx* c, int64_t n, int block, int per_sm = 8) {
     return (int)g;
 }
 
+// CTAs that are resident at once: the grid of a kernel whose CTAs stride over tiles (a partial second wave would start
+// late and finish last)
+template <typename K>
+static int resident_grid(const csv_ctx* c, K kernel, int block, size_t smem) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
+    return c->n_sm * std::max(per_sm, 1);
+}
+
 static int bits_for(uint64_t max_value) {
     int b = 0;
     while (b < 64 && (max_value >> b) != 0) b++;
@@ -938,10 +947,10 @@ static int run_indel(csv_ctx* c, int t, uint32_t kslot_base) {
         if (c->ticket_next >= (int)LB_ORDINALS) return set_err(CSV_E_STATE, "ticket pool exhausted");
         BigBuckets BB{c->big_bkt.as<uint4>(), bb_cap, c->tickets.as<uint32_t>() + c->ticket_next++};
         {
-            const int g = (int)std::min<uint32_t>(n_tiles, (uint32_t)c->n_sm * 8);
+            int g = (int)std::min<uint32_t>(n_tiles, (uint32_t)c->n_sm * 8);
             if (c->ticket_next >= (int)LB_ORDINALS) return set_err(CSV_E_STATE, "ticket pool exhausted");
             uint32_t* done_ctr = c->tickets.as<uint32_t>() + c->ticket_next++;
-#define BP_LAUNCH(RB) LAUNCH_PDL(c, (k_bucket_prefix<RB>), g, 256, 0, c->bkt.as<uint32_t>(), n_buckets, rb, (uint32_t)J.cp.min_support, bpre, tile_base, BB, &ctr->status, done_ctr, n_pass)
+#define BP_LAUNCH(RB) g = std::min(g, resident_grid(c, k_bucket_prefix<RB>, 256, 0)); LAUNCH_PDL(c, (k_bucket_prefix<RB>), g, 256, 0, c->bkt.as<uint32_t>(), n_buckets, rb, (uint32_t)J.cp.min_support, bpre, tile_base, BB, &ctr->status, done_ctr, n_pass)
             switch (rb) {
                 case 1: BP_LAUNCH(1); break; case 2: BP_LAUNCH(2); break; case 3: BP_LAUNCH(3); break; case 4: BP_LAUNCH(4); break;
                 case 5: BP_LAUNCH(5); break; case 6: BP_LAUNCH(6); break; case 7: BP_LAUNCH(7); break; case 8: BP_LAUNCH(8); break;
@@ -1303,12 +1312,12 @@ static int enqueue_cluster(csv_ctx* c, uint32_t type_mask) {
                 PB.pairs4 = c->pairs.as<uint4>();
                 PB.count = &ctr->n_windows;
                 if (G.lin32) {
-                    LAUNCH_PDL(c, (k_reads_pass<true>), grid_for(c, c->n_reads, 1024, 8), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                    LAUNCH_PDL(c, (k_reads_pass<true>), std::min(grid_for(c, c->n_reads, 1024, 8), resident_grid(c, k_reads_pass<true>, 256, 0)), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
                            c->r_end.as<int32_t>(), c->r_id.as<int32_t>(), c->r_prim.as<uint8_t>(), c->n_reads, &ctr->status);
                     LAUNCH_PDL(c, (k_pairs_test<true>), c->n_sm * 8, 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
                            c->r_end.as<int32_t>(), c->r_id.as<int32_t>());
                 } else {
-                    LAUNCH_PDL(c, (k_reads_pass<false>), grid_for(c, c->n_reads, 1024, 8), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
+                    LAUNCH_PDL(c, (k_reads_pass<false>), std::min(grid_for(c, c->n_reads, 1024, 8), resident_grid(c, k_reads_pass<false>, 256, 0)), 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
                            c->r_end.as<int32_t>(), c->r_id.as<int32_t>(), c->r_prim.as<uint8_t>(), c->n_reads, &ctr->status);
                     LAUNCH_PDL(c, (k_pairs_test<false>), c->n_sm * 8, 256, 0, G, PB, c->r_chrom.as<int32_t>(), c->r_start.as<int32_t>(),
                            c->r_end.as<int32_t>(), c->r_id.as<int32_t>());

@@ -1250,19 +1250,35 @@ __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const
         const int64_t base = tile * 256 * ITEMS;
         int32_t ch[ITEMS], st[ITEMS], en[ITEMS];
         uint8_t pr[ITEMS];
+        // row of item j: four consecutive rows per thread (one 128-bit load per column) when the columns allow it
+        const int64_t r0 = base + (int64_t)threadIdx.x * ITEMS;
+        const bool vec = ITEMS == 4 && r0 + ITEMS <= n_reads &&
+                         ((((uintptr_t)r_chrom) | ((uintptr_t)r_start) | ((uintptr_t)r_end)) & 15) == 0 && (((uintptr_t)r_prim) & 3) == 0;
+        const bool blocked = __syncthreads_and(vec || r0 >= n_reads) != 0;   // one mapping per tile (uniform: the pair slots are reserved per CTA)
+#define RP_ROW(j) (blocked ? r0 + (j) : base + (int64_t)(j) * 256 + threadIdx.x)
+        if (blocked && vec) {
+            const int4 c4 = __ldcs(reinterpret_cast<const int4*>(r_chrom + r0)), s4 = __ldcs(reinterpret_cast<const int4*>(r_start + r0));
+            const int4 e4 = __ldcs(reinterpret_cast<const int4*>(r_end + r0));
+            const uint32_t p4 = __ldcs(reinterpret_cast<const uint32_t*>(r_prim + r0));
+            ch[0] = c4.x; ch[1] = c4.y; ch[2] = c4.z; ch[3] = c4.w;
+            st[0] = s4.x; st[1] = s4.y; st[2] = s4.z; st[3] = s4.w;
+            en[0] = e4.x; en[1] = e4.y; en[2] = e4.z; en[3] = e4.w;
+            pr[0] = (uint8_t)p4; pr[1] = (uint8_t)(p4 >> 8); pr[2] = (uint8_t)(p4 >> 16); pr[3] = (uint8_t)(p4 >> 24);
+        } else {
 #pragma unroll
-        for (int j = 0; j < ITEMS; j++) {
-            const int64_t r = base + j * 256 + threadIdx.x;
-            const bool in = r < n_reads;
-            ch[j] = in ? __ldcs(r_chrom + r) : -1; st[j] = in ? __ldcs(r_start + r) : 0; en[j] = in ? __ldcs(r_end + r) : 0;
-            pr[j] = in ? __ldcs(r_prim + r) : 0;
+            for (int j = 0; j < ITEMS; j++) {
+                const int64_t r = RP_ROW(j);
+                const bool in = r < n_reads;
+                ch[j] = in ? __ldcs(r_chrom + r) : -1; st[j] = in ? __ldcs(r_start + r) : 0; en[j] = in ? __ldcs(r_end + r) : 0;
+                pr[j] = in ? __ldcs(r_prim + r) : 0;
+            }
         }
         uint32_t w[ITEMS], cnt[ITEMS], total = 0;
         uint64_t lin[ITEMS];   // RS of the read
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             w[j] = 0; cnt[j] = 0; lin[j] = 0;
-            const int64_t r = base + j * 256 + threadIdx.x;
+            const int64_t r = RP_ROW(j);
             if (r >= n_reads) continue;
             if (ch[j] < 0 || ch[j] >= G.ct.n) { atomicOr(status, ST_BAD_CHROM); continue; }
             uint64_t off;
@@ -1295,7 +1311,7 @@ __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             if (!cnt[j]) continue;
-            const int64_t r = base + j * 256 + threadIdx.x;
+            const int64_t r = RP_ROW(j);
             const int32_t rid = r_id[r];
             const uint64_t RS = lin[j], RE = lin[j] + (uint64_t)(uint32_t)(en[j] - st[j]);
             // slots below the capacity go to the pair buffer (every reserved slot < cap MUST be written:
@@ -1311,6 +1327,7 @@ __global__ void __launch_bounds__(256) k_reads_pass(GenoJob G, PairBuf PB, const
             }
             o += cnt[j];
         }
+#undef RP_ROW
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n_tab; i += 256)
