@@ -424,6 +424,8 @@ def main():
                      M=np.mean([ctrs["members"][k] for k in indel]) if indel else 0.0,
                      R=float(len(cfg["reads"]["chrom"])), C=float(n_cand) / n_types, P=float(ctrs["pairs"]), B=lin_total / 256.0)
             nbytes = kernel_bytes(nm, q)
+            if nm.startswith("k_rs_") and len(cfg["sigs"]) > len(indel):
+                nbytes = None   # launches of very different sizes under one name (INS/DEL passes + the small types' passes): no per-launch figure
             avg_ms = ms / n_l
             kernels[nm] = {"launches_per_step": per_launch, "avg_us": 1e3 * avg_ms, "ms_per_step": ms / args.steps,
                            "algorithmic_bytes_per_launch": nbytes,

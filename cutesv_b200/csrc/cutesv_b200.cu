@@ -229,6 +229,9 @@ struct csv_ctx {
     int rank = 0, world = 1;
     DBuf g_send, g_recv, g_cand, g_geno, g_names, g_scratch, g_tab;
     bool pdl_enabled = true;            // programmatic dependent launches along the kernel chain (CUTESV_B200_PDL=0: off)
+    bool pdl_now = false;               // ... for the call being enqueued: only with <= 2 SV-type lanes.  A dependent that is resident
+                                        // early holds SM slots while it waits; with 5 lanes sharing the GPU those slots are what the
+                                        // other lanes' kernels need (measured: config 2 -0.8 %, config 3 +3.8 %, config 5 +9 % step time)
     bool prev_is_chain_kernel = false;  // the launch being enqueued directly follows a chain kernel on the same stream
     DBuf cal_in0, cal_in1, cal_out, aln_flag;   // csv_cal_gl / csv_upload_alignments scratch (no per-call cudaMalloc)
     int64_t pad_cand = 0, pad_names = 0;
@@ -253,7 +256,7 @@ static void kprof_end(csv_ctx* c);
 // of its predecessor.  Captured into the CUDA graph as a programmatic edge.  Off when profiling (events sit between launches).
 #define LAUNCH_PDL_NAMED(ctx, name, kernel, grid, block, smem, ...)                                          \
     do {                                                                                                      \
-        if ((ctx)->pdl_enabled && !(ctx)->profiling) {                                                        \
+        if ((ctx)->pdl_now && !(ctx)->profiling) {                                                            \
             cudaLaunchConfig_t cfg_;                                                                          \
             memset(&cfg_, 0, sizeof(cfg_));                                                                   \
             cfg_.gridDim = dim3((unsigned)(grid)); cfg_.blockDim = dim3((unsigned)(block));                   \
@@ -1198,6 +1201,11 @@ static int enqueue_cluster(csv_ctx* c, uint32_t type_mask) {
     stage_reset_if_consumed(c);
     c->last_mask = type_mask;
     c->ticket_next = 0;
+    {
+        int n_lanes = 0;
+        for (int t = 0; t < CSV_NTYPES; t++) n_lanes += ((type_mask >> t & 1) && c->sig[t].n > 0) ? 1 : 0;
+        c->pdl_now = c->pdl_enabled && n_lanes <= 2;
+    }
     // fresh look-back generation, zeroed tickets and counters.  (The per-cluster row counts `cnt` need no clearing: every
     // kept-cluster slot below n_kept[t] is written by a cluster kernel and the order scans stop at n_kept[t].)
     LAUNCH(c, k_begin, 1, 256, 0, c->d_epoch.as<uint32_t>(), c->tickets.as<uint32_t>(), (int)LB_ORDINALS, c->counters.as<uint32_t>(),

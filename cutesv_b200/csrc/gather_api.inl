@@ -423,8 +423,6 @@ static int p2p_setup(csv_ctx* c, int64_t msg_bytes) {
 static int gather_enqueue(csv_ctx* c) {
     const GatherLayout L = gather_layout(c->pad_cand, c->pad_names, c->n_contigs, c->world);
     const int W = c->world;
-    CU(c->g_send.ensure((size_t)L.msg_bytes));
-    CU(c->g_recv.ensure((size_t)L.msg_bytes * W));
     CU(c->g_scratch.ensure((size_t)(W * GH_WORDS + 8) * 8, true));   // compact headers + status word (zero when allocated)
     CU(c->g_cand.ensure((size_t)L.pad_cand * W * sizeof(csv_cand) + 64));
     CU(c->g_geno.ensure((size_t)L.pad_cand * W * sizeof(csv_geno) + 64));
@@ -457,6 +455,8 @@ static int gather_enqueue(csv_ctx* c) {
         M.epoch = X.epoch;
     } else {
         // clear the key table -> pack -> ONE ncclAllGather -> merge
+        CU(c->g_send.ensure((size_t)L.msg_bytes));
+        CU(c->g_recv.ensure((size_t)L.msg_bytes * W));
         if (L.n_keys) CU(cudaMemsetAsync(c->g_send.as<char>() + L.off_tab, 0, (size_t)L.n_keys * 8, c->stream));
         LAUNCH(c, k_gather_pack, c->n_sm * 2, 256, 0, c->cand.as<csv_cand>(), c->geno.as<csv_geno>(), c->names.as<int32_t>(),
                c->counters.as<Counters>(), c->cap_cand, c->cap_names, L, c->rank, c->g_send.as<char>());
@@ -470,6 +470,7 @@ static int gather_enqueue(csv_ctx* c) {
     M.hdr = c->g_scratch.as<int64_t>();
     const size_t gm_smem = (size_t)L.n_keys * (W + 1) * 4;
     if (gm_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_gather_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm_smem));
+    c->pdl_now = c->pdl_enabled;   // one stream, the merge directly behind the push
     if (M.flags) LAUNCH_PDL(c, k_gather_merge, grid_for(c, std::max<int64_t>(L.pad_cand * W, L.pad_names), 256, 2), 256, gm_smem, M);   // behind k_gather_pack_push
     else LAUNCH(c, k_gather_merge, grid_for(c, std::max<int64_t>(L.pad_cand * W, L.pad_names), 256, 2), 256, gm_smem, M);
     CU(cudaMemcpyAsync(c->h_gather, M.hdr, (size_t)(W * GH_WORDS + 1) * 8, cudaMemcpyDeviceToHost, c->stream));

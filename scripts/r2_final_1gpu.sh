@@ -26,3 +26,6 @@ timeout 1200 ncu --set full --import-source on --clock-control none \
 tail -1 gpurun_out/ncu_full.log
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_extract -s 3 -c 1 -f -o gpurun_out/r02_full_extract python scripts/bench_extract.py 15000 7000 > gpurun_out/ncu_extract.log 2>&1
 tail -1 gpurun_out/ncu_extract.log
+unset CUTESV_B200_GRAPHS
+timeout 900 python scripts/bench_cli.py 1000000 --genotype --profile > gpurun_out/r02_cli_1m.json 2> gpurun_out/r02_cli_1m.err || tail -5 gpurun_out/r02_cli_1m.err
+tail -1 gpurun_out/r02_cli_1m.json

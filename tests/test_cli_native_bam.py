@@ -46,6 +46,9 @@ def test_cli_native_bam_dataset1_cpu(tmp_path):
     lines, gold, wd = _run(EmulEngine(), tmp_path, 1, ["--retain_work_dir"])
     assert lines == gold
     assert os.path.exists(os.path.join(wd, "reads.pickle"))
+    st = cli.main_ctrl.last_stages   # the stage split of the wall time that scripts/bench_cli.py reports
+    assert {"scan", "names_and_ties", "cluster_and_fetch", "rows", "vcf", "scan.csv_extract_append", "scan.ins_sequences"} <= set(st)
+    assert all(v >= 0 for v in st.values()) and st["scan"] >= st["scan.csv_extract_append"]
 
 
 def test_cli_native_bam_config1_cpu(tmp_path):
