@@ -39,4 +39,11 @@ rn = sorted(set(r.query_name for r in rd))
 pk = packing.pack_alignments(rd, {x: i for i, x in enumerate(cn)}, {x: i for i, x in enumerate(rn)})
 e.set_params(_abi.default_params(min_support=2, min_mapq=0, min_read_len=100, genotype=1)); e.set_contigs(cl)
 e.extract(pk); e.cluster_device(0x1F); n += len(e.fetch()[0])
+# append-mode extraction (two packets into the device-resident columns), read-id remap, repeated calls (CUDA graph capture + replay)
+e.extract_reset()
+e.extract(pk, append=True); e.extract(pk, append=True)
+e.remap_read_ids(np.arange(len(rn), dtype=np.int32))
+for _ in range(3):
+    e.cluster_device(0x1F)
+n += len(e.fetch()[0])
 print("sanitize run ok, candidates:", n)
