@@ -74,7 +74,52 @@ def records_to_rows(cands, genos, names_buf, chrom_names, read_name, ins_seq, ac
 
     Candidates flagged CSV_F_NO_READS are dropped (call_gt returns [] when the contig has no
     reads-table rows, resolveINDEL.py:443-444).
+    Same rows as record_to_row() per candidate; the record fields are taken out of the structured arrays column by
+    column first (one .tolist() per field instead of ~25 numpy scalar accesses per candidate).
     """
+    out = {}
+    n = len(cands)
+    if n == 0:
+        return out
+    f = {k: cands[k].tolist() for k in ("svtype", "chrom", "pos", "len", "support", "cipos", "cilen", "aux", "pos2", "names_off", "names_cnt", "flags")}
+    g_status, g_dr, g_gt, g_gq, g_qual = (genos[k].tolist() for k in ("status", "dr", "gt", "gq", "qual"))
+    g_pl = genos["pl"].tolist()
+    ids_all = names_buf.tolist() if hasattr(names_buf, "tolist") else list(names_buf)
+    svt, chrom_id, flags = f["svtype"], f["chrom"], f["flags"]
+    for i in range(n):
+        t = svt[i]
+        chrom = chrom_names[chrom_id[i]]
+        rows = out.setdefault((TYPE_NAMES[t], chrom), [])
+        if action and (flags[i] & CSV_F_NO_READS):
+            continue
+        o = f["names_off"][i]
+        names = ",".join([read_name(k) for k in ids_all[o:o + f["names_cnt"][i]]])
+        if not action or g_status[i] != 0:
+            dr, gt, gl, gq, qual = ".", "./.", ".,.,.", ".", "."
+        else:
+            pl = g_pl[i]
+            dr, gt, gl, gq, qual = str(g_dr[i]), GT_STR[g_gt[i]], "%d,%d,%d" % (pl[0], pl[1], pl[2]), str(g_gq[i]), str(float(g_qual[i]))
+        pos, ln, sup, aux = str(f["pos"][i]), str(f["len"][i]), str(f["support"][i]), f["aux"][i]
+        if t == CSV_DEL or t == CSV_INS:
+            ci, cl = f["cipos"][i], f["cilen"][i]
+            row = [chrom, TYPE_NAMES[t], pos, ln, sup, "-%d,%d" % (ci, ci), "-%d,%d" % (cl, cl), dr, gt, gl, gq, qual, names]
+            if t == CSV_INS:
+                row.append(ins_seq(aux)[0:f["len"][i]])
+        elif t == CSV_DUP:
+            row = [chrom, "DUP", pos, ln, sup, dr, gt, gl, gq, qual, names]
+        elif t == CSV_INV:
+            row = [chrom, "INV", pos, ln, sup, dr, gt, "++" if aux == 0 else "--", gl, gq, qual, names]
+        elif t == CSV_TRA:
+            chr2 = chrom_names[aux >> 2]
+            row = [chrom, tra_alt(TRA_TYPES[aux & 3], chr2, f["pos2"][i]), pos, chr2, str(f["pos2"][i]), sup, dr, gt, gl, gq, qual, names]
+        else:
+            raise ValueError("bad svtype %d" % t)
+        rows.append(row)
+    return out
+
+
+def records_to_rows_slow(cands, genos, names_buf, chrom_names, read_name, ins_seq, action):
+    """records_to_rows through record_to_row(), one candidate at a time (kept as the cross-check of the column-wise version)."""
     out = {}
     for i in range(len(cands)):
         c = cands[i]
