@@ -2,6 +2,8 @@
     python -m oracle.sweep cluster LO HI     kernel-template emulator (tests/emul) vs the C oracle, adversarial inputs x {preset, random flags}
     python -m oracle.sweep reference LO HI   the C oracle vs the live reference's rows on the same inputs
     python -m oracle.sweep extract LO HI [long]   emulator of kernel (a) vs the live reference's parse_read
+    python -m oracle.sweep cli LO HI         the reference's own main_ctrl (fake pysam) vs cutesv_b200.cli on a real BAM of the same records
+                                             (native decoder + emulator engine), VCF bodies; 4 flag sets, INS ties on every third seed
 Prints every mismatch and a summary line.  Two mismatch classes of `reference` are documented deviations:
 INS rows tying on (contig, int(pos), len, read) in arbitrary input order, and the reference's own KeyError in overlap_cover
 on a zero-width window (zero-length DUP, only with -l 0)."""
@@ -63,10 +65,49 @@ def extract(seed, kind="short"):
     yield 0, compare_extract.diff_extract(ref_c, ref_r, gc, gr)
 
 
+def cli(seed):
+    import pickle
+    import re
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests", "fake_pysam"))
+    import pysam  # noqa: F401  (the fake one)
+    import bam_writer
+    from emul_engine import EmulEngine
+    from cutesv_b200 import bamio
+    from cutesv_b200 import cli as our_cli
+    from oracle import gen_cli_golden
+    m = ref_harness.modules()
+    from cuteSV.cuteSV_Description import parseArgs
+    bamio.build()
+    flag_sets = [gen_cli_golden.FLAGS, gen_cli_golden.FLAGS + ["-mi", "-1", "--report_readid"],
+                 gen_cli_golden.EXTRA_FLAG_SETS["cli_dataset1_hifi_readid"], gen_cli_golden.EXTRA_FLAG_SETS["cli_dataset1_nogt_noseq"]]
+    flags = flag_sets[seed % len(flag_sets)]
+    d = tempfile.mkdtemp()
+    bam, fa, out, wd = gen_cli_golden.materialise(d, seed, 0.5 if seed % 3 == 0 else 0.0)
+    argv = [bam, fa, out, wd] + flags
+    m["main"].main_ctrl(parseArgs(argv), argv)
+    ds = pickle.load(open(bam, "rb"))
+    order = {nm: i for i, (nm, _) in enumerate(ds["contigs"])}
+    real = os.path.join(d, "real.bam")
+    bam_writer.write_bam(real, ds["contigs"], sorted(ds["reads"], key=lambda r: (order[r.reference_name], r.reference_start)), extra_unmapped=2)
+    d2 = tempfile.mkdtemp()
+    os.mkdir(os.path.join(d2, "wd"))
+    argv2 = [real, fa, os.path.join(d2, "o.vcf"), os.path.join(d2, "wd")] + flags
+    our_cli.main_ctrl(our_cli.build_parser().parse_args(argv2), argv2, engine=EmulEngine())
+
+    def norm(line):   # RNAMES of DUP / TRA records come from Python set iteration in the reference (hash order)
+        if "SVTYPE=BND" in line or "SVTYPE=DUP" in line:
+            return re.sub(r"RNAMES=([^;\t]*)", lambda mm: "RNAMES=" + ",".join(sorted(mm.group(1).split(","))), line)
+        return line
+    ref = [norm(x) for x in open(out) if not x.startswith("##")]
+    got = [norm(x) for x in open(argv2[2]) if not x.startswith("##")]
+    yield 0, ([] if ref == got else ["%d vs %d lines; first difference: %r" % (len(ref), len(got), [(a, b) for a, b in zip(ref, got) if a != b][:1])])
+
+
 def main():
     mode, lo, hi = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
     extra = sys.argv[4:]
-    fn = {"cluster": cluster, "reference": reference, "extract": extract}[mode]
+    fn = {"cluster": cluster, "reference": reference, "extract": extract, "cli": cli}[mode]
     bad = n = 0
     t0 = time.time()
     for seed in range(lo, hi):
